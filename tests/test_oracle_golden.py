@@ -1,0 +1,181 @@
+"""The numpy oracle against the fixtures produced by running the reference
+(oracle/gen_golden.py).  CPU only; this is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, cosine
+from oracle import rnb_oracle as O
+from rnb_b200 import synth
+
+
+def ref_like_state_dicts(perturb):
+    """Weights rebuilt from the same seeds as gen_golden.build_reference_nets, using THIS repo's modules."""
+    from models import fields
+    torch.manual_seed(0)
+    conf = synth.WMASK_CONF
+    nerf = fields.NeRF(**conf["nerf"])
+    sdf = fields.SDFNetwork(**conf["sdf_network"])
+    var = fields.SingleVarianceNetwork(**conf["variance_network"])
+    col = fields.RenderingNetwork(**conf["rendering_network"])
+    if perturb:
+        synth.perturb_state_dict_(sdf, synth.SDF_NOISE, 5)
+        synth.perturb_state_dict_(col, synth.COLOR_NOISE, 6)
+        with torch.no_grad():
+            var.variance.fill_(synth.TRAINED_VARIANCE)
+    sd = lambda m: {k: v.detach().double().numpy() for k, v in m.state_dict().items()}
+    return sd(sdf), sd(col), float(var.variance), nerf, (sdf, col, var)
+
+
+def wsum(module):
+    return np.array([float(p.detach().double().sum()) for _, p in sorted(module.named_parameters())])
+
+
+def test_embed():
+    g = load_golden("embed")
+    assert np.allclose(O.embed(g["x"], 6), g["e6"], atol=2e-6)
+    assert np.allclose(O.embed(g["x"], 4), g["e4"], atol=2e-6)
+    assert np.allclose(O.embed(g["x4"], 10), g["e10"], atol=3e-4)   # 2^9 x in float32
+    # vjp/jvp are adjoint
+    rng = np.random.default_rng(0)
+    de = rng.standard_normal(g["e6"].shape)
+    gb = rng.standard_normal(g["x"].shape)
+    assert np.isclose((O.embed_vjp(g["x"], de, 6) * gb).sum(), (de * O.embed_jvp(g["x"], gb, 6)).sum())
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+def test_weights_reproduce(perturb):
+    g = load_golden("sdf_perturbed" if perturb else "sdf_init")
+    _, _, _, _, (sdf, col, var) = ref_like_state_dicts(perturb)
+    assert np.allclose(wsum(sdf), g["wsum"], rtol=0, atol=1e-9)
+    assert np.allclose(wsum(col), g["cwsum"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+def test_sdf_forward_gradient_backward(perturb):
+    g = load_golden("sdf_perturbed" if perturb else "sdf_init")
+    sdf_sd, col_sd, _, _, _ = ref_like_state_dicts(perturb)
+    Ws, bs = O.sdf_effective(sdf_sd)
+    out = O.sdf_forward(Ws, bs, g["x"])
+    assert rel_l2(out[:, 0], g["out"][:, 0]) < 2e-5
+    assert rel_l2(out[:, 1:], g["out"][:, 1:]) < 2e-5
+    grad = O.sdf_gradient(Ws, bs, g["x"])
+    assert rel_l2(grad, g["grad"]) < 2e-5
+    dWs, dbs = O.sdf_backward(Ws, bs, g["x"], g["ybar"], g["gbar"])
+    st = int(g["stride"])
+    for l in range(9):
+        dg, dv = O.weight_norm_vjp(sdf_sd[f"lin{l}.weight_g"], sdf_sd[f"lin{l}.weight_v"], dWs[l])
+        for nm, val in ((f"lin{l}.weight_g", dg), (f"lin{l}.weight_v", dv), (f"lin{l}.bias", dbs[l])):
+            ref = g["g_" + nm]
+            if float(g["n_" + nm]) < 1e-12:
+                assert np.abs(val).max() < 1e-9
+                continue
+            assert rel_l2(val.ravel()[::st], ref) < 5e-4, nm
+            assert abs(np.linalg.norm(val) / float(g["n_" + nm]) - 1) < 5e-4, nm
+    # albedo net
+    cWs = [O.weight_norm_fold(col_sd[f"lin{l}.weight_g"], col_sd[f"lin{l}.weight_v"]) for l in range(3)]
+    cbs = [col_sd[f"lin{l}.bias"] for l in range(3)]
+    alb = O.color_forward(cWs, cbs, g["x"], g["grad"], g["out"][:, 1:])
+    assert rel_l2(alb, g["albedo"]) < 1e-5
+    cdW, cdb, dn, df = O.color_backward(cWs, cbs, g["x"], g["grad"], g["out"][:, 1:], g["abar"])
+    assert rel_l2(dn, g["d_normals"]) < 1e-4
+    assert rel_l2(df, g["d_feat"]) < 1e-4
+    for l in range(3):
+        dg, dv = O.weight_norm_vjp(col_sd[f"lin{l}.weight_g"], col_sd[f"lin{l}.weight_v"], cdW[l])
+        for nm, val in ((f"lin{l}.weight_g", dg), (f"lin{l}.weight_v", dv), (f"lin{l}.bias", cdb[l])):
+            assert rel_l2(val.ravel()[::st], g["cg_" + nm]) < 5e-4, nm
+
+
+def test_sample_pdf_indices_bit_exact():
+    g = load_golden("sample_pdf")
+    samples, inds, cdf = O.sample_pdf_det(g["bins"], g["weights"], 16, cdf_override=g["cdf"])
+    assert np.array_equal(inds, g["inds"])                       # bit-exact given the same CDF
+    assert np.allclose(samples, g["samples"], atol=1e-6)
+    # own CDF (numpy cumsum order) stays within float32 rounding of ATen's
+    _, _, cdf_own = O.sample_pdf_det(g["bins"], g["weights"], 16)
+    assert np.abs(cdf_own - g["cdf"]).max() < 2e-6
+
+
+CASES = ["warmup_albedo", "warmup_noalbedo", "post_albedo", "post_noalbedo", "womask_anneal", "init_warmup_albedo"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_render_and_grads(case):
+    g = load_golden("render_" + case)
+    sdf_sd, col_sd, variance, _, _ = ref_like_state_dicts(not case.startswith("init"))
+    Ws, bs = O.sdf_effective(sdf_sd)
+    # hierarchical sampling, step by step against the captured reference tensors
+    z, steps = O.hierarchical_sample(Ws, bs, g["rays_o"], g["rays_d"], g["near"], g["far"], g["t_rand"])
+    for i, s in enumerate(steps):
+        assert np.abs(s["z_in"] - g[f"up{i}_z_in"]).max() < 2e-3, i
+        # indices bit-exact when fed the reference's own inputs
+        new_z, inds, cdf = O.up_sample(g["rays_o"], g["rays_d"], g[f"up{i}_z_in"], g[f"up{i}_sdf_in"], 16,
+                                       float(g[f"up{i}_inv_s"]))
+        # float32 cancellation in (prev_cdf - next_cdf) makes z noisy at the 3e-4 level where the pdf is
+        # flat (rays that miss); tolerance = the north_star 1e-3, the mean is far tighter
+        dz = np.abs(new_z - g[f"up{i}_new_z"])
+        assert dz.max() < 1e-3 and dz.mean() < 1e-4, (i, dz.max(), dz.mean())
+    dz = np.abs(z - g["z_vals"])
+    assert dz.max() < 2e-3 and dz.mean() < 2e-4, (dz.max(), dz.mean())
+    # fine pass on the reference's own z_vals
+    ret, cache = O.render_rnb(sdf_sd, col_sd, variance, g["rays_o"], g["rays_d"], g["near"], g["far"],
+                              g["lights_dir"], None, cos_anneal_ratio=float(g["r"]), warmup=bool(g["warmup"]),
+                              no_albedo=bool(g["no_albedo"]), z_vals=g["z_vals"])
+    for k in ("color_fine", "weight_sum", "weight_max", "weights", "cdf_fine", "gradients", "s_val"):
+        assert rel_l2(ret[k], g["out_" + k]) < 2e-4, k
+    assert np.array_equal(ret["inside_sphere"], g["out_inside_sphere"])
+    assert abs(ret["gradient_error"] / float(g["out_gradient_error"]) - 1) < 1e-4
+    loss, parts, grads, _ = O.train_step_grads(ret, cache, g["true_rgb"], g["mask_used"], 0.1, float(g["mask_weight"]))
+    assert abs(loss / float(g["loss"]) - 1) < 1e-4
+    st = int(g["stride"])
+    checked = 0
+    for k in g:
+        if not k.startswith("g_"):
+            continue
+        nm = k[2:]
+        key = "variance" if nm == "var.variance" else nm
+        val = np.asarray(grads[key]).ravel()
+        ref = g[k]
+        nref = float(g["n_" + nm])
+        if nref < 1e-12:
+            continue
+        assert cosine(val[::st], ref) > 0.9999, nm
+        assert rel_l2(val[::st], ref) < 3e-3, (nm, rel_l2(val[::st], ref))
+        checked += 1
+    assert checked >= (16 if bool(g["no_albedo"]) else 25)
+    if bool(g["no_albedo"]):
+        assert not any(k.startswith("g_color.") for k in g)     # colour net gets no grad (exp_runner.py:111-112)
+
+
+def test_grid():
+    g = load_golden("grid")
+    sdf_sd, _, _, _, (sdf, _, _) = ref_like_state_dicts(True)
+    assert np.allclose(wsum(sdf), g["wsum"], atol=1e-9)
+    Ws, bs = O.sdf_effective(sdf_sd)
+    axes = O.grid_axes(g["bmin"], g["bmax"], 512)
+    # ATen's CPU linspace is vectorised (base + step*lane, width depends on the host ISA), its CUDA one is
+    # start + step*i / end - step*(R-1-i); both agree with the scalar formula to 1 ulp
+    assert np.abs(axes[0] - g["axis512"]).max() <= 1.2e-7
+    assert axes[0][0] == g["axis512"][0] and axes[0][-1] == g["axis512"][-1]
+    u = O.extract_fields(Ws, bs, g["bmin"], g["bmax"], 32)
+    assert u.shape == (32, 32, 32) and u.dtype == np.float32
+    assert np.abs(u - g["u32"]).max() < 2e-5
+    slab = O.extract_fields(Ws, bs, g["bmin"], g["bmax"], 32, x_range=(8, 16))
+    assert np.array_equal(slab, u[8:16])
+    idx = g["idx512"]
+    X = axes[0][idx]
+    xx, yy, zz = np.meshgrid(X, X, X, indexing="ij")
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], -1)
+    u512 = -O.sdf_only(Ws, bs, pts)[:, 0].reshape(len(idx), len(idx), len(idx))
+    assert np.abs(u512 - g["u512"]).max() < 2e-5
+
+
+def test_background_nerf():
+    g = load_golden("background")
+    _, _, _, nerf, _ = ref_like_state_dicts(True)
+    synth.perturb_state_dict_(nerf, 0.02, 7)
+    assert np.allclose(wsum(nerf), g["nwsum"], atol=1e-9)
+    sd = {k: v.detach().double().numpy() for k, v in nerf.state_dict().items()}
+    a, rgb = O.nerf_forward(sd, g["nerf_pts"], g["nerf_dirs"])
+    assert rel_l2(a, g["nerf_alpha"]) < 1e-4
+    assert rel_l2(rgb, g["nerf_rgb"]) < 1e-4
