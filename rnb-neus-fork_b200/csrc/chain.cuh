@@ -1,0 +1,219 @@
+// Tile-major MLP chain machinery shared by the SDF / albedo / NeRF kernels.
+//
+// One CTA = 6 warps = 192 threads, two CTAs co-resident per SM (112 KB smem + 256 TMEM columns each), so one
+// CTA's tcgen05.mma phase overlaps the other's epilogue without explicit ping-pong code.
+//   warp 0   : weight producer  -- cp.async.bulk (UBLKCP) of pre-packed K=32 weight slices into a 3-slot ring
+//   warp 1   : MMA issuer       -- lane 0 issues tcgen05.mma (M=128, N<=256, K=16) from smem A x smem W into TMEM
+//   warps 2-5: epilogue         -- one thread per point row: tcgen05.ld the fp32 accumulator, bias + activation
+//                                  (+ derivative terms) in registers, write the next layer's A operand (fp16,
+//                                  "chunked" K-major image, see common.cuh) into smem and any streams to HBM.
+// A "chain" is a table of GEMM steps executed strictly in order for each 128-point tile; step s+1's A operand
+// is written by step s's epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace rnb {
+
+constexpr int TILE_M = 128;
+constexpr int RING_STAGES = 3;
+constexpr int STAGE_BYTES = 16384;        // K=32 slice of a 256-row operand
+constexpr int CHAIN_THREADS = 192;
+constexpr int MAX_STEPS = 24;
+constexpr int TMEM_COLS = 256;
+
+struct ChainStep {
+    uint32_t w_off;   // byte offset of the packed [n x k] fp16 weight image in the blob
+    uint16_t n;       // UMMA N (rows of the weight image), multiple of 16, <= 256
+    uint16_t k;       // K, multiple of 32
+};
+struct ChainTable {
+    int n_steps;
+    ChainStep steps[MAX_STEPS];
+};
+
+struct ChainSmem {
+    uint8_t* sA;
+    uint8_t* ring;
+    uint64_t* full;     // [RING_STAGES]
+    uint64_t* empty;    // [RING_STAGES]
+    uint64_t* acc_full;
+    uint64_t* a_ready;
+    uint32_t* tmem_slot;
+};
+
+__host__ __device__ constexpr int chain_smem_bytes(int a_cols) {
+    return a_cols * TILE_M * 2 + RING_STAGES * STAGE_BYTES + 128;
+}
+
+__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int a_cols) {
+    ChainSmem s;
+    s.sA = smem;
+    s.ring = smem + a_cols * TILE_M * 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s.ring + RING_STAGES * STAGE_BYTES);
+    s.full = bars;
+    s.empty = bars + RING_STAGES;
+    s.acc_full = bars + 2 * RING_STAGES;
+    s.a_ready = bars + 2 * RING_STAGES + 1;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RING_STAGES + 2);
+    return s;
+}
+
+// Called by all threads at kernel start.  Returns the TMEM base address.
+__device__ __forceinline__ uint32_t chain_setup(const ChainSmem& s) {
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RING_STAGES; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
+        mbar_init(s.acc_full, 1);
+        mbar_init(s.a_ready, TILE_M);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(s.tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *s.tmem_slot;
+}
+
+__device__ __forceinline__ void chain_teardown(const ChainSmem& s, uint32_t tmem) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// warp 0, one lane
+__device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTable& tab, const uint8_t* wblob, int n_my_tiles) {
+    uint32_t it = 0;
+    for (int t = 0; t < n_my_tiles; ++t) {
+        for (int st = 0; st < tab.n_steps; ++st) {
+            const uint32_t bytes = 64u * tab.steps[st].n;                 // 4 chunks x n rows x 16 B
+            const uint8_t* src = wblob + tab.steps[st].w_off;
+            const int nsl = tab.steps[st].k >> 5;
+            for (int ks = 0; ks < nsl; ++ks, ++it) {
+                const uint32_t slot = it % RING_STAGES, ph = (it / RING_STAGES) & 1;
+                mbar_wait(&s.empty[slot], ph ^ 1);
+                mbar_expect_tx(&s.full[slot], bytes);
+                bulk_g2s(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot]);
+            }
+        }
+    }
+}
+
+// warp 1, one lane
+__device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& tab, uint32_t tmem, int n_my_tiles) {
+    uint32_t it = 0, sig = 0;
+    const uint32_t a_base = smem_u32(s.sA);
+    const uint32_t ring_base = smem_u32(s.ring);
+    for (int t = 0; t < n_my_tiles; ++t) {
+        for (int st = 0; st < tab.n_steps; ++st, ++sig) {
+            const uint32_t n = tab.steps[st].n;
+            const uint32_t idesc = umma_idesc(TILE_M, n, FMT_F16, FMT_F16);
+            const int nsl = tab.steps[st].k >> 5;
+            mbar_wait(s.a_ready, sig & 1);
+            tc_fence_after();
+            for (int ks = 0; ks < nsl; ++ks, ++it) {
+                const uint32_t slot = it % RING_STAGES, ph = (it / RING_STAGES) & 1;
+                mbar_wait(&s.full[slot], ph);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint64_t ad = umma_desc(a_base + (uint32_t)(ks * 2 + j) * (2 * TILE_M * 16), TILE_M * 16, 128);
+                    const uint64_t bd = umma_desc(ring_base + slot * STAGE_BYTES + (uint32_t)j * (2 * n * 16), n * 16, 128);
+                    umma_f16(tmem, ad, bd, idesc, (ks | j) != 0);
+                }
+                umma_commit(&s.empty[slot]);
+            }
+            umma_commit(s.acc_full);
+        }
+    }
+}
+
+// per-thread epilogue context (warps 2..5)
+struct Epi {
+    uint8_t* sA;
+    uint64_t* acc_full;
+    uint64_t* a_ready;
+    uint32_t tmem_row;   // TMEM address of this warp's lane quadrant, column 0
+    uint32_t acc_cnt;
+    int row;             // 0..127 = TMEM lane = point row inside the tile
+
+    __device__ __forceinline__ void init(const ChainSmem& s, uint32_t tmem) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int quad = warp & 3;           // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        sA = s.sA;
+        acc_full = s.acc_full;
+        a_ready = s.a_ready;
+        tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
+        row = quad * 32 + lane;
+        acc_cnt = 0;
+    }
+    __device__ __forceinline__ void wait_acc() {
+        mbar_wait(acc_full, acc_cnt & 1);
+        ++acc_cnt;
+        tc_fence_after();
+    }
+    // "A operand written, accumulator drained": lets the MMA warp start the next step
+    __device__ __forceinline__ void signal() {
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(a_ready);
+    }
+    __device__ __forceinline__ void st_a(int chunk, uint4 v) const {
+        *reinterpret_cast<uint4*>(sA + ((size_t)chunk * TILE_M + row) * 16) = v;
+    }
+    __device__ __forceinline__ void st_a_half(int col, __half h) const {
+        *reinterpret_cast<__half*>(sA + ((size_t)(col >> 3) * TILE_M + row) * 16 + (col & 7) * 2) = h;
+    }
+    __device__ __forceinline__ void ld_acc(int c0, uint32_t (&v)[32]) const {
+        tmem_ld32(tmem_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+    }
+};
+
+// ---- global "stream" images: [n_pts/64 subtiles][C/8 chunks][64 rows][16 B]  (data layout)
+__device__ __forceinline__ size_t stream_off(int64_t p, int chunk, int nchunks) {
+    return ((size_t)((p >> 6) * nchunks + chunk) * 64 + (size_t)(p & 63)) * 16;
+}
+__device__ __forceinline__ void st_stream(uint8_t* base, int64_t p, int chunk, int nchunks, uint4 v) {
+    *reinterpret_cast<uint4*>(base + stream_off(p, chunk, nchunks)) = v;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint8_t* base, int64_t p, int chunk, int nchunks) {
+    return *reinterpret_cast<const uint4*>(base + stream_off(p, chunk, nchunks));
+}
+
+// ---- activations (fp32, MUFU based)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus(beta=100): a = log(1+exp(100 z))/100  (reference models/fields.py:80).  The ATen threshold branch
+// (100 z > 20 -> a = z) differs from this closed form by < 2.1e-11, far below fp32 resolution of a.
+__device__ __forceinline__ float softplus100(float z) {
+    const float t = 100.f * z;
+    const float e = ex2_approx(-fabsf(t) * 1.4426950408889634f);
+    return fmaxf(z, 0.f) + lg2_approx(1.f + e) * 0.0069314718055994531f;   // ln2 / 100
+}
+// a = softplus(z), s = softplus'(z) = sigmoid(100 z)
+__device__ __forceinline__ void softplus100_ds(float z, float& a, float& s) {
+    const float t = 100.f * z;
+    const float e = ex2_approx(-fabsf(t) * 1.4426950408889634f);
+    const float q = 1.f + e;
+    const float r = rcp_approx(q);
+    a = fmaxf(z, 0.f) + lg2_approx(q) * 0.0069314718055994531f;
+    s = t >= 0.f ? r : e * r;
+}
+
+}  // namespace rnb

@@ -1,0 +1,563 @@
+// SDF MLP kernels (reference models/fields.py:82-127 and its autograd double-backward, exp_runner.py:261):
+//   sdf_fwd_kernel<GRID>      K1/K8  PE + 8 hidden layers, sdf = <a_7, W_8[0,:]> + b_8[0]        (no_grad evals, grid)
+//   sdf_fwd_grad_kernel       K2     forward + feature layer + analytic dx-chain, saves the streams K3 needs
+//   sdf_bwd_data_kernel       K3a    adjoint of the dx-chain (phase A) + ordinary backward (phase B); writes the
+//                                    cotangent streams the dW GEMM (dw_gemm.cu) contracts over the points
+// All GEMMs are tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate in TMEM); see chain.cuh for the CTA anatomy.
+#include "chain.cuh"
+#include "pe.cuh"
+#include "sdf_params.h"
+
+namespace rnb {
+
+constexpr int SDF_A_COLS = 256;
+constexpr int SKIP_COL = 217;      // layer 3 has 217 outputs; columns 217..255 of layer 4's input are the PE
+
+__device__ __forceinline__ void load_bias8(const float* b, float (&bb)[8]) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(b) + 1);
+    bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+    bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+}
+
+// fp16 image of the 64-wide layer-0 input: [x_hi(3) | sin/cos(36) | x_lo(3) | 0...]; x = x_hi + x_lo keeps the
+// linear term of the SDF at fp32-like accuracy although the operands are fp16.
+__device__ __forceinline__ void build_in0(const float (&x)[3], const SinCos<6>& sc, uint32_t (&h)[32]) {
+    float e[64];
+    pe_embed<6>(x, sc, e);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float hi = __half2float(__float2half_rn(x[j]));
+        e[39 + j] = x[j] - hi;
+    }
+#pragma unroll
+    for (int i = 42; i < 64; ++i) e[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) h[i] = pack_h2(e[2 * i], e[2 * i + 1]);
+}
+
+__device__ __forceinline__ void load_point(const SdfPointSource& src, int64_t p, float (&x)[3]) {
+    if (src.grid_res > 0) {
+        // u[ix,iy,iz] with ix = slab_x0 + p / R^2 : torch.linspace arithmetic of extract_fields
+        // (reference models/renderer.py:12-14): start + step*i for the lower half, end - step*(R-1-i) above.
+        const int R = src.grid_res;
+        int64_t q = p < src.n_pts ? p : src.n_pts - 1;
+        const int iz = (int)(q % R);
+        q /= R;
+        const int iy = (int)(q % R);
+        const int ix = (int)(q / R) + src.slab_x0;
+        const int idx[3] = {ix, iy, iz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float lo = src.bmin[a], hi = src.bmax[a];
+            const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(R - 1));
+            x[a] = idx[a] < R / 2 ? __fadd_rn(lo, __fmul_rn(step, (float)idx[a]))
+                                  : __fsub_rn(hi, __fmul_rn(step, (float)(R - 1 - idx[a])));
+        }
+    } else if (src.rays_o != nullptr) {
+        // point = o + d * z  (reference models/renderer.py:863, 181); z may be a section mid-point
+        const int64_t q = p < src.n_pts ? p : src.n_pts - 1;
+        const int64_t ray = q / src.n_per_ray;
+        const float z = __ldg(src.z + q);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = __ldg(src.rays_o + ray * 3 + a) + __ldg(src.rays_d + ray * 3 + a) * z;
+    } else {
+        const int64_t q = p < src.n_pts ? p : src.n_pts - 1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = __ldg(src.x + q * 3 + a);
+    }
+}
+
+// ======================================================================================= K1 / K8
+// One hidden layer's epilogue: z = acc + b, a = softplus(z) -> next A operand.  LAST also reduces the sdf row.
+template <bool LAST>
+__device__ __forceinline__ float fwd_layer_plain(const Epi& ep, const float* bias, const float* w8row) {
+    float acc = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t v[32];
+        ep.ld_acc(c0, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float bb[8], ww[8];
+            load_bias8(bias + c0 + q * 8, bb);
+            if (LAST) load_bias8(w8row + c0 + q * 8, ww);
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a[j] = softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]);
+                if (LAST) acc = fmaf(a[j], ww[j], acc);
+            }
+            if (!LAST) {
+                uint4 h;
+                h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
+                ep.st_a((c0 >> 3) + q, h);
+            }
+        }
+    }
+    return acc;
+}
+
+// overwrite columns 217..255 of the A operand (and optionally a global stream) with 39 values
+template <class F>
+__device__ __forceinline__ void write_skip_cols(const Epi& ep, F&& val, uint8_t* stream, int64_t p) {
+    // chunk 27 holds columns 216..223: keep column 216
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const __half h = __float2half_rn(val(i));
+        ep.st_a_half(SKIP_COL + i, h);
+        if (stream) *reinterpret_cast<__half*>(stream + stream_off(p, 27, 32) + (1 + i) * 2) = h;
+    }
+#pragma unroll
+    for (int c = 28; c < 32; ++c) {
+        const int i0 = c * 8 - SKIP_COL;
+        uint4 h;
+        h.x = pack_h2(val(i0 + 0), val(i0 + 1)); h.y = pack_h2(val(i0 + 2), val(i0 + 3));
+        h.z = pack_h2(val(i0 + 4), val(i0 + 5)); h.w = pack_h2(val(i0 + 6), val(i0 + 7));
+        ep.st_a(c, h);
+        if (stream) st_stream(stream, p, c, 32, h);
+    }
+}
+
+__device__ __forceinline__ void write_in0(const Epi& ep, const uint32_t (&h)[32], uint8_t* stream, int64_t p) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 u = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+        ep.st_a(c, u);
+        if (stream) st_stream(stream, p, c, 8, u);
+    }
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_kernel(const __grid_constant__ SdfFwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const ChainSmem s = chain_carve(smem, SDF_A_COLS);
+    const uint32_t tmem = chain_setup(s);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (warp == 0) {
+        if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
+    } else if (warp == 1) {
+        if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
+    } else {
+        Epi ep;
+        ep.init(s, tmem);
+        const float* bias = P.aux;
+        const float* w8row = P.aux + AUX_W8ROW;
+        const float b8 = __ldg(P.aux + AUX_B8_0);
+        for (int t = 0; t < n_my; ++t) {
+            const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
+            float x[3];
+            load_point(P.src, p, x);
+            SinCos<6> sc;
+            sc.compute(x[0], x[1], x[2]);
+            {
+                uint32_t h[32];
+                build_in0(x, sc, h);
+                write_in0(ep, h, nullptr, p);
+            }
+            ep.signal();
+            float sdf = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < 8; ++l) {
+                ep.wait_acc();
+                if (l < 7) {
+                    fwd_layer_plain<false>(ep, bias + l * 256, w8row);
+                    if (l == 3) {
+                        float e[39];
+                        pe_embed<6>(x, sc, e);
+                        write_skip_cols(ep, [&](int i) { return e[i]; }, nullptr, p);
+                    }
+                    ep.signal();
+                } else {
+                    sdf = fwd_layer_plain<true>(ep, bias + l * 256, w8row) + b8;
+                }
+            }
+            if (p < P.src.n_pts) P.out[p] = P.out_scale * sdf;
+        }
+    }
+    chain_teardown(s, tmem);
+}
+
+// ======================================================================================= K2
+__global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __grid_constant__ SdfFwdGradParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const ChainSmem s = chain_carve(smem, SDF_A_COLS);
+    const uint32_t tmem = chain_setup(s);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (warp == 0) {
+        if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
+    } else if (warp == 1) {
+        if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
+    } else {
+        Epi ep;
+        ep.init(s, tmem);
+        const float* bias = P.aux;
+        const float* w8row = P.aux + AUX_W8ROW;
+        const float b8 = __ldg(P.aux + AUX_B8_0);
+        const size_t SS = P.stream_stride;
+        for (int t = 0; t < n_my; ++t) {
+            const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
+            const bool live = p < P.src.n_pts;
+            float x[3];
+            load_point(P.src, p, x);
+            SinCos<6> sc;
+            sc.compute(x[0], x[1], x[2]);
+            {
+                uint32_t h[32];
+                build_in0(x, sc, h);
+                write_in0(ep, h, P.st_in0, p);
+            }
+            ep.signal();
+            // ---------------- forward, layers 0..7: a_l -> A and stream in_{l+1}; s_l -> stream
+            float sdf = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < 8; ++l) {
+                ep.wait_acc();
+                uint8_t* st_a_next = P.st_in + (size_t)l * SS;       // in_{l+1} = a_l
+                uint8_t* st_s = P.st_s + (size_t)l * SS;
+                const float* bl = bias + l * 256;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    ep.ld_acc(c0, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float bb[8], ww[8];
+                        load_bias8(bl + c0 + q * 8, bb);
+                        if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
+                        float a[8], sg[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            softplus100_ds(__uint_as_float(v[q * 8 + j]) + bb[j], a[j], sg[j]);
+                            if (l == 7) sdf = fmaf(a[j], ww[j], sdf);
+                        }
+                        uint4 ha, hs;
+                        ha.x = pack_h2(a[0], a[1]); ha.y = pack_h2(a[2], a[3]); ha.z = pack_h2(a[4], a[5]); ha.w = pack_h2(a[6], a[7]);
+                        hs.x = pack_h2(sg[0], sg[1]); hs.y = pack_h2(sg[2], sg[3]); hs.z = pack_h2(sg[4], sg[5]); hs.w = pack_h2(sg[6], sg[7]);
+                        const int ch = (c0 >> 3) + q;
+                        ep.st_a(ch, ha);
+                        st_stream(st_a_next, p, ch, 32, ha);
+                        st_stream(st_s, p, ch, 32, hs);
+                    }
+                }
+                if (l == 3) {
+                    float e[39];
+                    pe_embed<6>(x, sc, e);
+                    write_skip_cols(ep, [&](int i) { return e[i]; }, st_a_next, p);
+                    // s_3 = 0 on the skip columns, so w_3 = 0 there in the dx-chain and in K3
+                    uint8_t* z = st_s + stream_off(p, 27, 32);
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) *reinterpret_cast<__half*>(z + i * 2) = __float2half_rn(0.f);
+#pragma unroll
+                    for (int c = 28; c < 32; ++c) st_stream(st_s, p, c, 32, make_uint4(0, 0, 0, 0));
+                }
+                ep.signal();
+            }
+            sdf += b8;
+            if (live) P.out_sdf[p] = sdf;
+            // ---------------- layer 8 features; then seed the dx-chain: w_7 = s_7 * W_8[0,:]
+            ep.wait_acc();
+            {
+                const float* b8f = bias + 8 * 256;
+                const uint8_t* st_s7 = P.st_s + (size_t)7 * SS;
+                uint8_t* st_w7 = P.st_w + (size_t)7 * SS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    ep.ld_acc(c0, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float bb[8], ww[8];
+                        load_bias8(b8f + c0 + q * 8, bb);
+                        load_bias8(w8row + c0 + q * 8, ww);
+                        const int ch = (c0 >> 3) + q;
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]) + bb[j];
+                        uint4 hf;
+                        hf.x = pack_h2(f[0], f[1]); hf.y = pack_h2(f[2], f[3]); hf.z = pack_h2(f[4], f[5]); hf.w = pack_h2(f[6], f[7]);
+                        st_stream(P.st_feat, p, ch, 32, hf);
+                        if (P.out_full && live) {
+                            float* o = P.out_full + (size_t)p * 257 + 1 + c0 + q * 8;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = f[j];
+                        }
+                        const uint4 hs = ld_stream(st_s7, p, ch, 32);
+                        const float2 s0 = unpack_h2(hs.x), s1 = unpack_h2(hs.y), s2 = unpack_h2(hs.z), s3 = unpack_h2(hs.w);
+                        uint4 hw;
+                        hw.x = pack_h2(s0.x * ww[0], s0.y * ww[1]); hw.y = pack_h2(s1.x * ww[2], s1.y * ww[3]);
+                        hw.z = pack_h2(s2.x * ww[4], s2.y * ww[5]); hw.w = pack_h2(s3.x * ww[6], s3.y * ww[7]);
+                        ep.st_a(ch, hw);
+                        st_stream(st_w7, p, ch, 32, hw);
+                    }
+                }
+                if (P.out_full && live) P.out_full[(size_t)p * 257] = sdf;
+            }
+            ep.signal();
+            // ---------------- dx-chain: GEMM l (= 7..1) yields ua_{l-1}; w_{l-1} = s_{l-1} * ua_{l-1}
+            float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int l = 7; l >= 1; --l) {
+                ep.wait_acc();
+                const uint8_t* st_sp = P.st_s + (size_t)(l - 1) * SS;
+                uint8_t* st_wp = P.st_w + (size_t)(l - 1) * SS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    ep.ld_acc(c0, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ch = (c0 >> 3) + q;
+                        const uint4 hs = ld_stream(st_sp, p, ch, 32);
+                        const float2 s0 = unpack_h2(hs.x), s1 = unpack_h2(hs.y), s2 = unpack_h2(hs.z), s3 = unpack_h2(hs.w);
+                        float u[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) u[j] = __uint_as_float(v[q * 8 + j]);
+                        uint4 hw;
+                        hw.x = pack_h2(s0.x * u[0], s0.y * u[1]); hw.y = pack_h2(s1.x * u[2], s1.y * u[3]);
+                        hw.z = pack_h2(s2.x * u[4], s2.y * u[5]); hw.w = pack_h2(s3.x * u[6], s3.y * u[7]);
+                        ep.st_a(ch, hw);
+                        st_stream(st_wp, p, ch, 32, hw);
+                    }
+                }
+                if (l == 4) {
+                    // uin_4[217:] is d sdf / d e through the skip connection: fold it into the gradient now
+                    uint32_t v[32];
+                    ep.ld_acc(192, v);
+#pragma unroll
+                    for (int j = SKIP_COL - 192; j < 32; ++j) pe_vjp_col<6>(192 + j - SKIP_COL, sc, __uint_as_float(v[j]), g);
+                    ep.ld_acc(224, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pe_vjp_col<6>(224 + j - SKIP_COL, sc, __uint_as_float(v[j]), g);
+                }
+                ep.signal();
+            }
+            // ---------------- last dx GEMM (N = 64): uin_0 = d sdf / d e
+            ep.wait_acc();
+            {
+                uint32_t v[32];
+                ep.ld_acc(0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pe_vjp_col<6>(j, sc, __uint_as_float(v[j]), g);
+                ep.ld_acc(32, v);
+#pragma unroll
+                for (int j = 0; j < 7; ++j) pe_vjp_col<6>(32 + j, sc, __uint_as_float(v[j]), g);
+            }
+            if (live) {
+                P.out_grad[p * 3 + 0] = g[0];
+                P.out_grad[p * 3 + 1] = g[1];
+                P.out_grad[p * 3 + 2] = g[2];
+            }
+            // the next tile's prologue signals; nothing to do here
+        }
+    }
+    chain_teardown(s, tmem);
+}
+
+// ======================================================================================= K3a
+__device__ __forceinline__ float cot_scale_from_max(float m) {
+    // power of two that maps the largest input cotangent to [128, 256): keeps every fp16 cotangent operand
+    // far from overflow (x256 headroom) while the small ones stay in the normal range
+    if (!(m > 0.f) || !isfinite(m)) return 1.f;
+    int e;
+    frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 8 - e);
+}
+
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __grid_constant__ SdfBwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const ChainSmem s = chain_carve(smem, SDF_A_COLS);
+    const uint32_t tmem = chain_setup(s);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (warp == 0) {
+        if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
+    } else if (warp == 1) {
+        if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
+    } else {
+        Epi ep;
+        ep.init(s, tmem);
+        const float* w8row = P.aux + AUX_W8ROW;
+        const size_t SS = P.stream_stride;
+        const float scale = cot_scale_from_max(__ldg(P.cot_absmax));
+        for (int t = 0; t < n_my; ++t) {
+            const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
+            const bool live = p < P.src.n_pts;
+            float x[3];
+            load_point(P.src, p, x);
+            SinCos<6> sc;
+            sc.compute(x[0], x[1], x[2]);
+            float gb[3] = {0.f, 0.f, 0.f};
+            float dsdf = 0.f;
+            if (live) {
+                gb[0] = __ldg(P.d_grad + p * 3 + 0) * scale;
+                gb[1] = __ldg(P.d_grad + p * 3 + 1) * scale;
+                gb[2] = __ldg(P.d_grad + p * 3 + 2) * scale;
+                dsdf = __ldg(P.d_sdf + p) * scale;
+            }
+            // uin_0 = J_e gbar in the 64-wide layer-0 column layout (x_lo columns carry no cotangent)
+            {
+                uint32_t h[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float e0 = 2 * i < 39 ? pe_jvp_col<6>(2 * i, sc, gb) : 0.f;
+                    const float e1 = 2 * i + 1 < 39 ? pe_jvp_col<6>(2 * i + 1, sc, gb) : 0.f;
+                    h[i] = pack_h2_sat(e0, e1);
+                }
+                write_in0(ep, h, P.st_uin0, p);
+            }
+            ep.signal();
+            // ---------------- phase A, l = 0..7:  wbar = W_l uin_l ;  z2_l = 100(1-s)w*wbar ;  ua_bar = s*wbar
+#pragma unroll 1
+            for (int l = 0; l < 8; ++l) {
+                ep.wait_acc();
+                const uint8_t* st_s = P.st_s + (size_t)l * SS;
+                const uint8_t* st_w = P.st_w + (size_t)l * SS;
+                uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
+                uint8_t* st_un = P.st_uin + (size_t)l * SS;          // uin_{l+1} = ua_bar_l
+#pragma unroll 1
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    ep.ld_acc(c0, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ch = (c0 >> 3) + q;
+                        const uint4 hs = ld_stream(st_s, p, ch, 32);
+                        const uint4 hw = ld_stream(st_w, p, ch, 32);
+                        const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hwa[4] = {hw.x, hw.y, hw.z, hw.w};
+                        uint32_t z2[4], ub[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 sv = unpack_h2(hsa[j]), wv = unpack_h2(hwa[j]);
+                            const float wb0 = __uint_as_float(v[q * 8 + 2 * j]), wb1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
+                            z2[j] = pack_h2_sat(100.f * (1.f - sv.x) * wv.x * wb0, 100.f * (1.f - sv.y) * wv.y * wb1);
+                            ub[j] = pack_h2_sat(sv.x * wb0, sv.y * wb1);
+                        }
+                        const uint4 uz = make_uint4(z2[0], z2[1], z2[2], z2[3]);
+                        const uint4 uu = make_uint4(ub[0], ub[1], ub[2], ub[3]);
+                        st_stream(st_z2, p, ch, 32, uz);
+                        st_stream(st_un, p, ch, 32, uu);
+                        if (l < 7) ep.st_a(ch, uu);
+                    }
+                }
+                if (l == 3) {
+                    // uin_4 = cat[ua_bar_3, ebar]  (the 1/sqrt2 lives in the packed W_4)
+                    float e[39];
+#pragma unroll
+                    for (int i = 0; i < 39; ++i) e[i] = pe_jvp_col<6>(i, sc, gb);
+                    write_skip_cols(ep, [&](int i) { return fminf(fmaxf(e[i], -65504.f), 65504.f); }, st_un, p);
+                }
+                if (l == 7) {
+                    // A operand of phase B's first GEMM: d_feat (scaled, fp16); also streamed for dW_8
+#pragma unroll 1
+                    for (int ch = 0; ch < 32; ++ch) {
+                        float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
+                        if (live) {
+                            const float4* src = reinterpret_cast<const float4*>(P.d_feat + (size_t)p * 256 + ch * 8);
+                            f0 = __ldg(src);
+                            f1 = __ldg(src + 1);
+                        }
+                        uint4 h;
+                        h.x = pack_h2_sat(f0.x * scale, f0.y * scale); h.y = pack_h2_sat(f0.z * scale, f0.w * scale);
+                        h.z = pack_h2_sat(f1.x * scale, f1.y * scale); h.w = pack_h2_sat(f1.z * scale, f1.w * scale);
+                        ep.st_a(ch, h);
+                        st_stream(P.st_dfeat, p, ch, 32, h);
+                    }
+                }
+                ep.signal();
+            }
+            // ---------------- phase B: GEMM yields abar_l (l = 7..0);  zbar_l = s_l*abar_l + z2_l
+#pragma unroll 1
+            for (int l = 7; l >= 0; --l) {
+                ep.wait_acc();
+                const uint8_t* st_s = P.st_s + (size_t)l * SS;
+                const uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
+                uint8_t* st_zb = P.st_zbar + (size_t)l * SS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t v[32];
+                    ep.ld_acc(c0, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ch = (c0 >> 3) + q;
+                        const uint4 hs = ld_stream(st_s, p, ch, 32);
+                        const uint4 hz = ld_stream(st_z2, p, ch, 32);
+                        const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
+                        float ww[8];
+                        if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
+                        uint32_t zb[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 sv = unpack_h2(hsa[j]), zv = unpack_h2(hza[j]);
+                            float a0 = __uint_as_float(v[q * 8 + 2 * j]), a1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
+                            if (l == 7) {   // abar_7 = d_feat W_8[1:,:] + d_sdf W_8[0,:]
+                                a0 = fmaf(dsdf, ww[2 * j], a0);
+                                a1 = fmaf(dsdf, ww[2 * j + 1], a1);
+                            }
+                            zb[j] = pack_h2_sat(fmaf(sv.x, a0, zv.x), fmaf(sv.y, a1, zv.y));
+                        }
+                        const uint4 uz = make_uint4(zb[0], zb[1], zb[2], zb[3]);
+                        st_stream(st_zb, p, ch, 32, uz);
+                        if (l > 0) ep.st_a(ch, uz);
+                    }
+                }
+                if (l > 0) ep.signal();
+            }
+        }
+    }
+    chain_teardown(s, tmem);
+}
+
+// ======================================================================================= launchers
+static inline int chain_grid(int n_tiles, int sm_count) {
+    const int g = 2 * sm_count;
+    return n_tiles < g ? n_tiles : g;
+}
+
+cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    const int smem = chain_smem_bytes(SDF_A_COLS);
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(sdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (P.n_tiles == 0) return cudaSuccess;
+    sdf_fwd_kernel<<<chain_grid(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sdf_fwd_grad(const SdfFwdGradParams& P, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    const int smem = chain_smem_bytes(SDF_A_COLS);
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(sdf_fwd_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (P.n_tiles == 0) return cudaSuccess;
+    sdf_fwd_grad_kernel<<<chain_grid(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sdf_bwd_data(const SdfBwdParams& P, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    const int smem = chain_smem_bytes(SDF_A_COLS);
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(sdf_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (P.n_tiles == 0) return cudaSuccess;
+    sdf_bwd_data_kernel<<<chain_grid(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace rnb

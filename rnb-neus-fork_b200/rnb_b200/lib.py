@@ -1,0 +1,78 @@
+"""ctypes binding of librnb_b200.so (C ABI in include/rnb_b200.h).
+
+The library is the product: there is no Python/CPU fallback.  Importing this module without the built
+shared object, or calling a kernel without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librnb_b200.so")
+
+
+class Points(C.Structure):
+    """rnb_points_t"""
+    _fields_ = [("n_pts", C.c_int64), ("x", C.c_void_p), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p),
+                ("z", C.c_void_p), ("n_per_ray", C.c_int32), ("grid_res", C.c_int32), ("slab_x0", C.c_int32),
+                ("bmin", C.c_float * 3), ("bmax", C.c_float * 3)]
+
+
+_lib = None
+
+_VP = C.c_void_p
+_SIGNATURES = {
+    "rnb_error_string": (C.c_char_p, [C.c_int]),
+    "rnb_version": (C.c_int, []),
+    "rnb_sdf_wblob_bytes": (C.c_size_t, []),
+    "rnb_sdf_aux_floats": (C.c_size_t, []),
+    "rnb_padded_points": (C.c_int64, [C.c_int64]),
+    "rnb_stream_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "rnb_sdf_pack": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP), _VP, _VP, _VP]),
+    "rnb_sdf_fwd": (C.c_int, [C.POINTER(Points), _VP, _VP, _VP, C.c_float, _VP]),
+    "rnb_sdf_fwd_grad": (C.c_int, [C.POINTER(Points)] + [_VP] * 11),
+}
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(f"rnb_b200: {LIB_PATH} is missing -- build it with __graft_entry__.build() "
+                               "(rnb-neus-fork_b200/csrc/build.sh); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise RuntimeError(f"rnb_b200.{what} failed: {load().rnb_error_string(code).decode()} ({code})")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "rnb_b200 kernels take contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"rnb_b200.{what}: the hot path runs only on CUDA (sm_100a); got a {t.device} tensor. "
+                           "There is no CPU fallback -- move the module and inputs to a B200.")

@@ -1,0 +1,51 @@
+"""GPU parity of the SDF kernels (through the C ABI) against the numpy oracle and the golden fixtures.
+Tolerance: SDF / gradient <= 1e-3 relative in the norm (north_star); fp16 operands, fp32 accumulate."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from gpu_common import build_nets, np_state
+from oracle import rnb_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def packed_for(sdf):
+    from rnb_b200 import kernels as K
+    eff = sdf.effective_weights()
+    return K.SdfPacked("cuda").pack([w for w, _ in eff], [b for _, b in eff])
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+@pytest.mark.parametrize("n", [96, 1000, 5000])
+def test_sdf_fwd_and_grad(perturb, n):
+    from rnb_b200 import kernels as K
+    _, sdf, _, _ = build_nets(perturb)
+    pk = packed_for(sdf)
+    g = torch.Generator().manual_seed(n)
+    x = ((torch.rand(n, 3, generator=g) - 0.5) * 2.4).cuda()
+    Ws, bs = O.sdf_effective(np_state(sdf))
+    ref_out, ref_grad = O.sdf_gradient(Ws, bs, x.cpu().numpy(), keep=True)[:2]
+    out = K.sdf_fwd(pk, K.points_explicit(x)).cpu().numpy()
+    assert rel_l2(out, ref_out[:, 0]) < TOL
+    s, gr, full, st = K.sdf_fwd_grad(pk, K.points_explicit(x), want_full=True)
+    torch.cuda.synchronize()
+    assert rel_l2(s.cpu().numpy(), ref_out[:, 0]) < TOL
+    assert rel_l2(gr.cpu().numpy(), ref_grad) < TOL
+    assert rel_l2(full.cpu().numpy(), ref_out) < TOL
+    feat = K.stream_to_rowmajor(st.feat, n, 256).float().cpu().numpy()
+    assert rel_l2(feat, ref_out[:, 1:]) < 2e-3
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+def test_sdf_golden(perturb):
+    from rnb_b200 import kernels as K
+    gld = load_golden("sdf_perturbed" if perturb else "sdf_init")
+    _, sdf, _, _ = build_nets(perturb)
+    pk = packed_for(sdf)
+    x = torch.from_numpy(gld["x"]).cuda()
+    s, gr, full, _ = K.sdf_fwd_grad(pk, K.points_explicit(x), want_full=True)
+    assert rel_l2(full.cpu().numpy(), gld["out"]) < TOL
+    assert rel_l2(gr.cpu().numpy(), gld["grad"]) < TOL
