@@ -63,6 +63,17 @@ RNB_API int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float*
 RNB_API int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* aux, float* out_sdf, float* out_grad,
                      float* out_full, void* st_feat, void* st_in0, void* st_in, void* st_s, void* st_w, void* stream);
 
+/* Double-backward of (sdf, features, gradient) w.r.t. the effective weights (what loss.backward() does to
+ * SDFNetwork.forward + .gradient in the reference: exp_runner.py:261 through models/fields.py:82-127).
+ * Cotangents: d_sdf [n], d_grad [n,3], d_feat [n,256] fp32 row-major (d_feat may be NULL = zero).
+ * st_*: the streams written by rnb_sdf_fwd_grad for the same points.  scratch: rnb_sdf_bwd_scratch_bytes(n).
+ * dW, db: HOST arrays of 9 DEVICE pointers, dW[l] fp32 [out_l,in_l] row-major (256x39, 256x256, 256x256,
+ * 217x256, 256x256 x4, 257x256), db[l] [out_l]; overwritten. */
+RNB_API size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts);
+RNB_API int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
+                const float* d_feat, const void* st_in0, const void* st_in, const void* st_s, const void* st_w,
+                void* scratch, float* const* dW, float* const* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

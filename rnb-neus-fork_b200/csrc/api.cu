@@ -1,12 +1,46 @@
 // extern "C" boundary of librnb_b200.so (declarations and contracts: include/rnb_b200.h).
 #include "../../include/rnb_b200.h"
 #include "sdf_params.h"
+#include "dw_params.h"
+#include <algorithm>
 
 namespace rnb {
 cudaError_t launch_sdf_pack(const float* const* W, const float* const* b, uint8_t* blob, float* aux, cudaStream_t st);
 cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_sdf_fwd_grad(const SdfFwdGradParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_sdf_bwd_data(const SdfBwdParams& P, int sm_count, cudaStream_t st);
+cudaError_t launch_dw_gemm(const DwParams& P, int splits, cudaStream_t st);
+cudaError_t launch_colsum(const ColsumParams& P, int splits, cudaStream_t st);
+cudaError_t launch_reduce(const ReduceParams& P, cudaStream_t st);
+cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out,
+                          cudaStream_t st);
+cudaError_t launch_sum(const float* x, int64_t n, float* out, cudaStream_t st);
+
+// scratch layout of rnb_sdf_bwd
+struct SdfBwdScratch {
+    size_t absmax, uin0, uin, z2, zbar, dfeat, dw_part, cs_part, total;
+    int dw_splits, cs_splits;
+};
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
+    SdfBwdScratch L;
+    const size_t s256 = rnb_stream_bytes(n_pts, 256), s64 = rnb_stream_bytes(n_pts, 64);
+    const int n_sub = (int)(rnb_padded_points(n_pts) / 64);
+    L.dw_splits = std::max(1, std::min(n_sub, 48));
+    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 32));
+    size_t o = 0;
+    L.absmax = o; o += 256;
+    L.uin0 = o; o += s64;
+    L.uin = o; o += 8 * s256;
+    L.z2 = o; o += 8 * s256;
+    L.zbar = o; o += 8 * s256;
+    L.dfeat = o; o += s256;
+    o = align_up(o, 256);
+    L.dw_part = o; o += (size_t)L.dw_splits * 256 * (64 + 8 * 256) * 4;
+    L.cs_part = o; o += (size_t)L.cs_splits * 256 * 12 * 4;
+    L.total = align_up(o, 256);
+    return L;
+}
 
 static int sm_count() {
     static int n = 0;
@@ -83,6 +117,108 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
     P.st_s = (uint8_t*)st_s; P.st_w = (uint8_t*)st_w;
     P.stream_stride = rnb_stream_bytes(pts->n_pts, 256);
     return (int)launch_sdf_fwd_grad(P, sm_count(), (cudaStream_t)stream);
+}
+
+
+size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts) { return sdf_bwd_scratch(n_pts).total; }
+
+int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
+                const float* d_feat, const void* st_in0, const void* st_in, const void* st_s, const void* st_w,
+                void* scratch, float* const* dW, float* const* db, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = pts->n_pts;
+    if (n <= 0) return 0;
+    const SdfBwdScratch L = sdf_bwd_scratch(n);
+    uint8_t* sc = (uint8_t*)scratch;
+    float* absmax = (float*)(sc + L.absmax);
+    const size_t SS = rnb_stream_bytes(n, 256);
+    cudaError_t e = launch_absmax(d_sdf, n, d_grad, 3 * n, d_feat, d_feat ? 256 * n : 0, absmax, st);
+    if (e != cudaSuccess) return (int)e;
+    // ---- K3a: cotangent streams
+    SdfBwdParams P{};
+    P.src = to_src(pts);
+    P.n_tiles = n_tiles(n);
+    P.wblob = (const uint8_t*)wblob;
+    P.aux = aux;
+    table_forward(P.tab);
+    add_step(P.tab, SDFW_T8, 256, 256);
+    for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256);
+    P.d_sdf = d_sdf; P.d_grad = d_grad; P.d_feat = d_feat; P.cot_absmax = absmax;
+    P.st_s = (const uint8_t*)st_s; P.st_w = (const uint8_t*)st_w;
+    P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_z2 = sc + L.z2; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;
+    P.stream_stride = SS;
+    e = launch_sdf_bwd_data(P, sm_count(), st);
+    if (e != cudaSuccess) return (int)e;
+    // ---- K3b: dW_l = w_l^T uin_l + zbar_l^T in_l  (l = 0..7),  dW_8[1:] = dfeat^T in_8
+    const int n_sub = (int)(rnb_padded_points(n) / 64);
+    DwParams D{};
+    D.n_sub = n_sub;
+    ReduceParams R{};
+    R.cot_absmax = absmax;
+    float* part = (float*)(sc + L.dw_part);
+    const uint8_t* in0 = (const uint8_t*)st_in0;
+    const uint8_t* inl = (const uint8_t*)st_in;
+    const uint8_t* sw = (const uint8_t*)st_w;
+    for (int l = 0; l < 9; ++l) {
+        DwJob& j = D.jobs[D.n_jobs++];
+        j.nw = l == 0 ? 64 : 256;
+        j.b_chunk0 = 0;
+        if (l < 8) {
+            j.n_pairs = 2;
+            j.a[0] = sw + (size_t)l * SS;
+            j.b[0] = l == 0 ? sc + L.uin0 : sc + L.uin + (size_t)(l - 1) * SS;
+            j.a[1] = sc + L.zbar + (size_t)l * SS;
+            j.b[1] = l == 0 ? in0 : inl + (size_t)(l - 1) * SS;
+        } else {
+            j.n_pairs = 1;
+            j.a[0] = sc + L.dfeat;
+            j.b[0] = inl + (size_t)7 * SS;
+        }
+        j.b_chunks[0] = j.b_chunks[1] = j.nw / 8;
+        j.partial = part;
+        ReduceJob& r = R.jobs[R.n_jobs++];
+        r.partial = part; r.splits = L.dw_splits; r.rows = 256; r.nw = j.nw;
+        r.dst = dW[l]; r.dst_pitch = l == 0 ? 39 : 256; r.dst_row0 = l == 8 ? 1 : 0; r.dst_col0 = 0;
+        r.out_rows = l == 3 ? 217 : 256; r.out_cols = l == 0 ? 39 : 256;
+        r.factor = l == 4 ? 0.70710678118654752f : 1.f;
+        r.use_cot_scale = 1; r.fold_xlo = l == 0; r.accumulate = 0;
+        part += (size_t)L.dw_splits * 256 * j.nw;
+    }
+    e = launch_dw_gemm(D, L.dw_splits, st);
+    if (e != cudaSuccess) return (int)e;
+    // ---- bias gradients and the sdf row of W_8 (column sums over streams)
+    ColsumParams C{};
+    C.n_sub = n_sub;
+    C.n_pts = n;
+    float* cpart = (float*)(sc + L.cs_part);
+    auto add_cs = [&](const uint8_t* stream, const float* wgt) {
+        ColsumJob& j = C.jobs[C.n_jobs++];
+        j.stream = stream; j.chunks = 32; j.row_weight = wgt; j.partial = cpart;
+        float* p0 = cpart;
+        cpart += (size_t)L.cs_splits * 256;
+        return p0;
+    };
+    for (int l = 0; l < 9; ++l) {
+        const float* p0 = add_cs(l < 8 ? sc + L.zbar + (size_t)l * SS : sc + L.dfeat, nullptr);
+        ReduceJob& r = R.jobs[R.n_jobs++];
+        r.partial = p0; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
+        r.dst = db[l]; r.dst_pitch = 0; r.dst_row0 = 0; r.dst_col0 = l == 8 ? 1 : 0;
+        r.out_rows = 1; r.out_cols = l == 3 ? 217 : 256; r.factor = 1.f; r.use_cot_scale = 1;
+    }
+    {
+        // dW_8[0,:] = sum_p uabar_7[p,:]  +  sum_p d_sdf[p] a_7[p,:]
+        const float* p0 = add_cs(sc + L.uin + (size_t)7 * SS, nullptr);
+        const float* p1 = add_cs(inl + (size_t)7 * SS, d_sdf);
+        ReduceJob& r = R.jobs[R.n_jobs++];
+        r.partial = p0; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
+        r.dst = dW[8]; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = 1;
+        r.partial2 = p1; r.splits2 = L.cs_splits; r.factor2 = 1.f; r.use_cot_scale2 = 0;
+    }
+    e = launch_colsum(C, L.cs_splits, st);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_reduce(R, st);
+    if (e != cudaSuccess) return (int)e;
+    return (int)launch_sum(d_sdf, n, db[8], st);
 }
 
 }  // extern "C"

@@ -1,0 +1,258 @@
+// Weight-gradient GEMMs: dW[256 x N] = sum over points of A_stream^T * B_stream (K = points).
+//   SDF layer l (reference autograd, SURVEY 8a' K3):  dW_l = w_l^T uin_bar_l + zbar_l^T in_l   (two stream pairs)
+// Both operands are read straight from the activation streams as MN-major SWIZZLE_NONE UMMA operands: a 64-point
+// stream sub-tile [chunk][64 rows][16 B] IS the canonical MN-major image (8 points x 8 columns = one 128-byte core
+// matrix), so one cp.async.bulk per operand per stage feeds tcgen05.mma with no transpose anywhere.
+// Split-K over the points; each CTA keeps a full 256 x N fp32 accumulator in TMEM (2 x 256 columns), dumps one
+// partial, and a small kernel reduces the partials deterministically.  HBM-bound by design (128 FLOP/B).
+#include "common.cuh"
+#include "dw_params.h"
+
+namespace rnb {
+
+constexpr int DW_THREADS = 192;
+constexpr int DW_STAGES = 3;
+constexpr int DW_STAGE_A = 32768;     // 64 points x 256 columns fp16
+constexpr int DW_STAGE_B = 32768;     // 64 points x <=256 columns fp16
+constexpr int DW_STAGE = DW_STAGE_A + DW_STAGE_B;
+constexpr int DW_SMEM = DW_STAGES * DW_STAGE + 128;
+
+__global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const __grid_constant__ DwParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DW_STAGES * DW_STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + DW_STAGES;
+    uint64_t* acc_full = bars + 2 * DW_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DW_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const DwJob& job = P.jobs[blockIdx.y];
+    const int split = blockIdx.x;
+    const int per = (P.n_sub + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int sub0 = split * per;
+    const int sub1 = min(P.n_sub, sub0 + per);
+    const int nw = job.nw;
+    const uint32_t b_bytes = (uint32_t)(nw >> 3) * 1024u;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int sub = sub0; sub < sub1; ++sub)
+                for (int pr = 0; pr < job.n_pairs; ++pr, ++it) {
+                    const uint32_t slot = it % DW_STAGES, ph = (it / DW_STAGES) & 1;
+                    mbar_wait(&empty[slot], ph ^ 1);
+                    mbar_expect_tx(&full[slot], DW_STAGE_A + b_bytes);
+                    uint8_t* dst = smem + slot * DW_STAGE;
+                    bulk_g2s(dst, job.a[pr] + (size_t)sub * DW_STAGE_A, DW_STAGE_A, &full[slot]);
+                    bulk_g2s(dst + DW_STAGE_A, job.b[pr] + ((size_t)sub * job.b_chunks[pr] + job.b_chunk0) * 1024u, b_bytes,
+                             &full[slot]);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(128, nw, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
+            uint32_t it = 0;
+            for (int sub = sub0; sub < sub1; ++sub)
+                for (int pr = 0; pr < job.n_pairs; ++pr, ++it) {
+                    const uint32_t slot = it % DW_STAGES, ph = (it / DW_STAGES) & 1;
+                    mbar_wait(&full[slot], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + slot * DW_STAGE), sb = sa + DW_STAGE_A;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            // MN-major: LBO = next 8-point group (128 B), SBO = next 8-column chunk (64 rows x 16 B)
+                            const uint64_t ad = umma_desc(sa + h * 16384 + ks * 256, 128, 1024);
+                            const uint64_t bd = umma_desc(sb + ks * 256, 128, 1024);
+                            umma_f16(tmem + h * 256, ad, bd, idesc, (it | ks) != 0);
+                        }
+                    umma_commit(&empty[slot]);
+                }
+            umma_commit(acc_full);
+        }
+    } else {
+        // epilogue: dump the two 128-row halves of the accumulator as one fp32 partial [256][nw]
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        float* out = job.partial + (size_t)split * 256 * nw;
+        if (sub1 > sub0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h)
+#pragma unroll 1
+                for (int c0 = 0; c0 < nw; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + h * 256 + c0, v);
+                    tmem_ld_wait();
+                    float4* dst = reinterpret_cast<float4*>(out + (size_t)(h * 128 + row) * nw + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+        } else {
+            for (int h = 0; h < 2; ++h)
+                for (int c = 0; c < nw; ++c) out[(size_t)(h * 128 + row) * nw + c] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------ column sums over a stream (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ ColsumParams P) {
+    const ColsumJob& job = P.jobs[blockIdx.z];
+    const int chunk = blockIdx.x;
+    if (chunk >= job.chunks) return;
+    const int split = blockIdx.y;
+    const int per = (P.n_sub + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int sub0 = split * per, sub1 = min(P.n_sub, sub0 + per);
+    const int r = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int sub = sub0 + sl; sub < sub1; sub += 4) {
+        const uint4 u = *reinterpret_cast<const uint4*>(job.stream + (((size_t)sub * job.chunks + chunk) * 64 + r) * 16);
+        float wgt = 1.f;
+        if (job.row_weight) {
+            const int64_t p = (int64_t)sub * 64 + r;
+            wgt = p < P.n_pts ? __ldg(job.row_weight + p) : 0.f;
+        }
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_h2(w[j]);
+            acc[2 * j] = fmaf(wgt, f.x, acc[2 * j]);
+            acc[2 * j + 1] = fmaf(wgt, f.y, acc[2 * j + 1]);
+        }
+    }
+    __shared__ float red[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        job.partial[(size_t)split * job.chunks * 8 + chunk * 8 + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------ deterministic reduction of split-K partials
+__global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ ReduceParams P) {
+    const ReduceJob& job = P.jobs[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= job.out_rows * job.out_cols) return;
+    const int m = idx / job.out_cols, n = idx % job.out_cols;
+    float inv_sc = 1.f;
+    {
+        const float mx = __ldg(P.cot_absmax);
+        if (mx > 0.f && isfinite(mx)) {
+            int e;
+            frexpf(mx, &e);
+            inv_sc = ldexpf(1.f, e - 8);
+        }
+    }
+    const float factor = job.use_cot_scale ? job.factor * inv_sc : job.factor;
+    float acc = 0.f;
+    const size_t stride = (size_t)job.rows * job.nw;
+    const float* src = job.partial + (size_t)m * job.nw + n;
+    for (int s = 0; s < job.splits; ++s) acc += src[(size_t)s * stride];
+    if (job.fold_xlo && n < 3) {
+        const float* src2 = job.partial + (size_t)m * job.nw + 39 + n;
+        for (int s = 0; s < job.splits; ++s) acc += src2[(size_t)s * stride];
+    }
+    acc *= factor;
+    if (job.partial2) {
+        float acc2 = 0.f;
+        const float* s2 = job.partial2 + (size_t)m * job.nw + n;
+        for (int s = 0; s < job.splits2; ++s) acc2 += s2[(size_t)s * stride];
+        acc += acc2 * (job.use_cot_scale2 ? job.factor2 * inv_sc : job.factor2);
+    }
+    float* dst = job.dst + (size_t)(job.dst_row0 + m) * job.dst_pitch + job.dst_col0 + n;
+    *dst = job.accumulate ? *dst + acc : acc;
+}
+
+// ------------------------------------------------------------------ max |x| over up to three fp32 arrays
+__global__ void absmax_kernel(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
+                              float* out) {
+    float m = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
+    for (int64_t i = i0; i < nb; i += stride) m = fmaxf(m, fabsf(b[i]));
+    for (int64_t i = i0; i < nc; i += stride) m = fmaxf(m, fabsf(c[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
+// sum of a small fp32 array (d b_8[0] = sum d_sdf)
+__global__ void __launch_bounds__(1024) sum_kernel(const float* x, int64_t n, float* out) {
+    float v = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) v += x[i];
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *out = v;
+    }
+}
+cudaError_t launch_sum(const float* x, int64_t n, float* out, cudaStream_t st) {
+    sum_kernel<<<1, 1024, 0, st>>>(x, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dw_gemm(const DwParams& P, int splits, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (P.n_jobs == 0) return cudaSuccess;
+    dw_gemm_kernel<<<dim3(splits, P.n_jobs), DW_THREADS, DW_SMEM, st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_colsum(const ColsumParams& P, int splits, cudaStream_t st) {
+    if (P.n_jobs == 0) return cudaSuccess;
+    colsum_kernel<<<dim3(40, splits, P.n_jobs), 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_reduce(const ReduceParams& P, cudaStream_t st) {
+    if (P.n_jobs == 0) return cudaSuccess;
+    int mx = 0;
+    for (int j = 0; j < P.n_jobs; ++j) mx = max(mx, P.jobs[j].out_rows * P.jobs[j].out_cols);
+    reduce_kernel<<<dim3((mx + 255) / 256, P.n_jobs), 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out,
+                          cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    absmax_kernel<<<296, 256, 0, st>>>(a, na, b, nb, c, nc, out);
+    return cudaGetLastError();
+}
+
+}  // namespace rnb

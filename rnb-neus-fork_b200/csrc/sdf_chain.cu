@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
 #pragma unroll 1
                     for (int ch = 0; ch < 32; ++ch) {
                         float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
-                        if (live) {
+                        if (live && P.d_feat) {
                             const float4* src = reinterpret_cast<const float4*>(P.d_feat + (size_t)p * 256 + ch * 8);
                             f0 = __ldg(src);
                             f1 = __ldg(src + 1);

@@ -117,6 +117,31 @@ def sdf_fwd_grad(packed: SdfPacked, pts, streams: SdfStreams = None, want_full=F
     return sdf, grad, full, streams
 
 
+SDF_W_SHAPES = [(256, 39), (256, 256), (256, 256), (217, 256), (256, 256), (256, 256), (256, 256), (256, 256), (257, 256)]
+
+
+def sdf_bwd(packed: SdfPacked, pts, streams: SdfStreams, d_sdf, d_grad, d_feat=None, scratch=None):
+    """-> (dWs, dbs): gradients w.r.t. the effective (weight-norm folded) weights and biases."""
+    dev = packed.wblob.device
+    lib = L.load()
+    n = pts.n_pts
+    need = lib.rnb_sdf_bwd_scratch_bytes(n)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    d_sdf = d_sdf.detach().float().contiguous().view(-1)
+    d_grad = d_grad.detach().float().contiguous().view(-1, 3)
+    if d_feat is not None:
+        d_feat = d_feat.detach().float().contiguous().view(-1, 256)
+    dWs = [torch.empty(s, dtype=torch.float32, device=dev) for s in SDF_W_SHAPES]
+    dbs = [torch.empty(s[0], dtype=torch.float32, device=dev) for s in SDF_W_SHAPES]
+    wp = (C.c_void_p * N_SDF_LAYERS)(*[L.ptr(t) for t in dWs])
+    bp = (C.c_void_p * N_SDF_LAYERS)(*[L.ptr(t) for t in dbs])
+    L.check(lib.rnb_sdf_bwd(C.byref(pts), L.ptr(packed.wblob), L.ptr(packed.aux), L.ptr(d_sdf), L.ptr(d_grad),
+                            L.ptr(d_feat), L.ptr(streams.in0), L.ptr(streams.inl), L.ptr(streams.s), L.ptr(streams.w),
+                            L.ptr(scratch), wp, bp, L.stream_ptr()), "sdf_bwd")
+    return dWs, dbs, scratch
+
+
 def stream_to_rowmajor(buf, n_pts, cols, dtype=torch.float16):
     """Decode a stream image [Npad/64][cols/8][64][8] into [n_pts, cols] (tests / debugging)."""
     t = buf.view(dtype).view(-1, cols // 8, 64, 8).permute(0, 2, 1, 3).reshape(-1, cols)

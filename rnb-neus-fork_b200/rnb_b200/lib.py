@@ -34,6 +34,8 @@ _SIGNATURES = {
     "rnb_sdf_pack": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP), _VP, _VP, _VP]),
     "rnb_sdf_fwd": (C.c_int, [C.POINTER(Points), _VP, _VP, _VP, C.c_float, _VP]),
     "rnb_sdf_fwd_grad": (C.c_int, [C.POINTER(Points)] + [_VP] * 11),
+    "rnb_sdf_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 10 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
 }
 
 

@@ -49,3 +49,32 @@ def test_sdf_golden(perturb):
     s, gr, full, _ = K.sdf_fwd_grad(pk, K.points_explicit(x), want_full=True)
     assert rel_l2(full.cpu().numpy(), gld["out"]) < TOL
     assert rel_l2(gr.cpu().numpy(), gld["grad"]) < TOL
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+@pytest.mark.parametrize("n", [200, 4000])
+def test_sdf_backward(perturb, n):
+    """Double-backward: parameter gradients cos >= 0.999 and rel-L2 <= 1e-2 (north_star)."""
+    from conftest import cosine
+    from rnb_b200 import kernels as K
+    _, sdf, _, _ = build_nets(perturb)
+    pk = packed_for(sdf)
+    g = torch.Generator().manual_seed(100 + n)
+    x = ((torch.rand(n, 3, generator=g) - 0.5) * 2.0).cuda()
+    # cotangent magnitudes like a real RNb loss (SURVEY 8a': d_sdf ~1e-6..1e-3, d_feat ~1e-10..1e-6)
+    d_sdf = (torch.randn(n, generator=g) * 1e-4 * torch.rand(n, generator=g) ** 4).cuda()
+    d_grad = (torch.randn(n, 3, generator=g) * 3e-5).cuda()
+    d_feat = (torch.randn(n, 256, generator=g) * 1e-7 * (torch.rand(n, 256, generator=g) > 0.33)).cuda()
+    pts = K.points_explicit(x)
+    _, _, _, st = K.sdf_fwd_grad(pk, pts)
+    dWs, dbs, _ = K.sdf_bwd(pk, pts, st, d_sdf, d_grad, d_feat)
+    torch.cuda.synchronize()
+    Ws, bs = O.sdf_effective(np_state(sdf))
+    ybar = np.concatenate([d_sdf.cpu().numpy()[:, None], d_feat.cpu().numpy()], 1)
+    rW, rb = O.sdf_backward(Ws, bs, x.cpu().numpy(), ybar, d_grad.cpu().numpy())
+    for l in range(9):
+        for nm, got, ref in ((f"dW{l}", dWs[l], rW[l]), (f"db{l}", dbs[l], rb[l])):
+            got = got.cpu().numpy()
+            assert np.isfinite(got).all(), nm
+            assert cosine(got, ref) > 0.999, (nm, cosine(got, ref))
+            assert rel_l2(got, ref) < 1e-2, (nm, rel_l2(got, ref))
