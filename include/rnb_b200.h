@@ -74,6 +74,76 @@ RNB_API int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float*
                 const float* d_feat, const void* st_in0, const void* st_in, const void* st_s, const void* st_w,
                 void* scratch, float* const* dW, float* const* db, void* stream);
 
+
+/* ---- per-ray kernels (reference models/renderer.py) ------------------------------------------------------- */
+
+/* one hierarchical up-sampling step: merge the samples drawn by the previous step (cat_z_vals, renderer.py:178-192),
+ * then up_sample (:132-176) + sample_pdf(det=True) (:39-69) -> n_new new depths per ray. */
+typedef struct {
+    int32_t n_rays;
+    const float* rays_o;        /* [B,3] */
+    const float* rays_d;        /* [B,3] */
+    const float* z_old;         /* [B,n_old] sorted */
+    const float* sdf_old;       /* [B,n_old] */
+    int32_t n_old;
+    const float* z_pending;     /* [B,n_merge] drawn by the previous step (merged first); may be NULL */
+    const float* sdf_pending;   /* [B,n_merge] */
+    int32_t n_merge;
+    float* z_merged;            /* [B,n_old+n_merge] out; may be NULL */
+    float* sdf_merged;
+    float inv_s;                /* 64 * 2^i (renderer.py:872) */
+    int32_t n_new;              /* <= 32 */
+    float* z_new;               /* [B,n_new] out */
+    int32_t* inds;              /* optional [B,n_new]: searchsorted indices */
+    float* cdf_out;             /* optional [B,n_old+n_merge] */
+} rnb_upsample_t;
+
+/* render_core_mvps after the networks + RNb shading sum (renderer.py:503-540, 904-918, 1008-1017) and its adjoint.
+ * 128 samples per ray.  Light l of ray b is read at lights + l*light_stride_l + b*light_stride_ray (floats). */
+typedef struct {
+    int32_t n_rays;
+    const float* rays_o;
+    const float* rays_d;
+    const float* z;             /* [B,128] */
+    const float* sdf;           /* [B*128] at the section mid-points */
+    const float* grad;          /* [B*128,3] */
+    const float* albedo;        /* [B*128,3] or NULL (no_albedo: ones) */
+    const float* lights;
+    int32_t n_lights;
+    int64_t light_stride_l, light_stride_ray;
+    const float* variance;      /* device scalar, SingleVarianceNetwork.variance */
+    float cos_anneal_ratio;
+    int32_t warmup;             /* 1 = relu on the shading (render_rnb_warmup) */
+    float sample_dist;          /* 2 / n_samples */
+    float* color;               /* out [L,B,3] */
+    float* weights;             /* out [B,128] */
+    float* cdf;                 /* out [B,128] */
+    float* inside;              /* out [B,128] */
+    float* weight_sum;          /* out [B] */
+    float* weight_max;          /* out [B] */
+    float* eik_part;            /* out [B,2] per-ray numerator / denominator of the eikonal term */
+    const float* d_color;       /* bwd in [L,B,3] */
+    const float* d_weight_sum;  /* bwd in [B] or NULL */
+    const float* d_eik;         /* bwd in, device scalar */
+    const float* eik_den;       /* bwd in, device scalar: sum of relax_inside_sphere */
+    float* d_sdf;               /* bwd out [B*128] */
+    float* d_grad;              /* bwd out [B*128,3] */
+    float* d_albedo;            /* bwd out [B*128,3] or NULL */
+    float* d_var_part;          /* bwd out [B] per-ray d loss / d variance */
+} rnb_composite_t;
+
+/* z = near + (far-near)*linspace(0,1,n) + t_rand*2/n   (renderer.py:829-845); t_rand may be NULL */
+RNB_API int rnb_coarse_z(const float* near, const float* far, const float* t_rand, float* z, int n_rays, int n_samples, void* stream);
+RNB_API int rnb_upsample_step(const rnb_upsample_t* p, void* stream);
+/* test hook for "searchsorted indices bit-exact given the same CDF": sample_pdf's inverse-CDF on a caller CDF */
+RNB_API int rnb_sample_pdf_from_cdf(const float* bins, const float* cdf, int n_rays, int n, int n_new, float* samples,
+                            int64_t* inds, void* stream);
+/* last cat_z_vals (z only) + section mid-points z + dist/2 (renderer.py:479-484) */
+RNB_API int rnb_final_merge(const float* z_old, int n_old, const float* z_new, int n_new, int n_rays, float sample_dist,
+                    float* z_out, float* mid_out, void* stream);
+RNB_API int rnb_composite_fwd(const rnb_composite_t* p, void* stream);
+RNB_API int rnb_composite_bwd(const rnb_composite_t* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 #include "../../include/rnb_b200.h"
 #include "sdf_params.h"
 #include "dw_params.h"
+#include "render_params.h"
 #include <algorithm>
 
 namespace rnb {
@@ -15,6 +16,14 @@ cudaError_t launch_reduce(const ReduceParams& P, cudaStream_t st);
 cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out,
                           cudaStream_t st);
 cudaError_t launch_sum(const float* x, int64_t n, float* out, cudaStream_t st);
+cudaError_t launch_coarse_z(const float* near, const float* far, const float* t_rand, float* z, int n_rays, int n_samples,
+                            cudaStream_t st);
+cudaError_t launch_upsample(const UpsampleParams& P, cudaStream_t st);
+cudaError_t launch_sample_pdf_from_cdf(const float* bins, const float* cdf, int n_rays, int n, int n_new, float* samples,
+                                       int64_t* inds, cudaStream_t st);
+cudaError_t launch_final_merge(const float* z_old, int n_old, const float* z_new, int n_new, int n_rays, float sample_dist,
+                               float* z_out, float* mid_out, cudaStream_t st);
+cudaError_t launch_composite(const CompositeParams& P, bool bwd, cudaStream_t st);
 
 // scratch layout of rnb_sdf_bwd
 struct SdfBwdScratch {
@@ -220,5 +229,25 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     if (e != cudaSuccess) return (int)e;
     return (int)launch_sum(d_sdf, n, db[8], st);
 }
+
+
+int rnb_coarse_z(const float* near, const float* far, const float* t_rand, float* z, int n_rays, int n_samples, void* stream) {
+    return (int)launch_coarse_z(near, far, t_rand, z, n_rays, n_samples, (cudaStream_t)stream);
+}
+int rnb_upsample_step(const rnb_upsample_t* p, void* stream) {
+    if (p->n_old + p->n_merge > MAX_RAY_SAMPLES || p->n_new > 32) return (int)cudaErrorInvalidValue;
+    return (int)launch_upsample(*p, (cudaStream_t)stream);
+}
+int rnb_sample_pdf_from_cdf(const float* bins, const float* cdf, int n_rays, int n, int n_new, float* samples, int64_t* inds,
+                            void* stream) {
+    return (int)launch_sample_pdf_from_cdf(bins, cdf, n_rays, n, n_new, samples, inds, (cudaStream_t)stream);
+}
+int rnb_final_merge(const float* z_old, int n_old, const float* z_new, int n_new, int n_rays, float sample_dist, float* z_out,
+                    float* mid_out, void* stream) {
+    if (n_old + n_new > MAX_RAY_SAMPLES) return (int)cudaErrorInvalidValue;
+    return (int)launch_final_merge(z_old, n_old, z_new, n_new, n_rays, sample_dist, z_out, mid_out, (cudaStream_t)stream);
+}
+int rnb_composite_fwd(const rnb_composite_t* p, void* stream) { return (int)launch_composite(*p, false, (cudaStream_t)stream); }
+int rnb_composite_bwd(const rnb_composite_t* p, void* stream) { return (int)launch_composite(*p, true, (cudaStream_t)stream); }
 
 }  // extern "C"

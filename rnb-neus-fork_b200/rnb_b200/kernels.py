@@ -142,6 +142,115 @@ def sdf_bwd(packed: SdfPacked, pts, streams: SdfStreams, d_sdf, d_grad, d_feat=N
     return dWs, dbs, scratch
 
 
+# ----------------------------------------------------------------------------- per-ray kernels
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def coarse_z(near, far, t_rand, n_samples):
+    near, far = _f32(near).view(-1), _f32(far).view(-1)
+    L.require_cuda(near, "coarse_z")
+    tr = _f32(t_rand).view(-1) if t_rand is not None else None
+    z = torch.empty(near.numel(), n_samples, dtype=torch.float32, device=near.device)
+    L.check(L.load().rnb_coarse_z(L.ptr(near), L.ptr(far), L.ptr(tr), L.ptr(z), near.numel(), n_samples, L.stream_ptr()),
+            "coarse_z")
+    return z
+
+
+def upsample_step(rays_o, rays_d, z_old, sdf_old, inv_s, n_new, z_pending=None, sdf_pending=None, want_merged=True,
+                  want_debug=False):
+    """-> (z_new [B,n_new], z_merged, sdf_merged, inds, cdf)"""
+    B, n_old = z_old.shape
+    n_merge = 0 if z_pending is None else z_pending.shape[1]
+    dev = z_old.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    z_new = torch.empty(B, n_new, **f32)
+    z_m = torch.empty(B, n_old + n_merge, **f32) if (want_merged and n_merge) else None
+    s_m = torch.empty(B, n_old + n_merge, **f32) if (want_merged and n_merge) else None
+    inds = torch.empty(B, n_new, dtype=torch.int32, device=dev) if want_debug else None
+    cdf = torch.empty(B, n_old + n_merge, **f32) if want_debug else None
+    p = L.Upsample()
+    p.n_rays = B
+    p.rays_o, p.rays_d = L.ptr(rays_o), L.ptr(rays_d)
+    p.z_old, p.sdf_old, p.n_old = L.ptr(z_old), L.ptr(sdf_old), n_old
+    p.z_pending, p.sdf_pending, p.n_merge = L.ptr(z_pending), L.ptr(sdf_pending), n_merge
+    p.z_merged, p.sdf_merged = L.ptr(z_m), L.ptr(s_m)
+    p.inv_s, p.n_new = float(inv_s), n_new
+    p.z_new, p.inds, p.cdf_out = L.ptr(z_new), L.ptr(inds), L.ptr(cdf)
+    L.check(L.load().rnb_upsample_step(C.byref(p), L.stream_ptr()), "upsample_step")
+    if not n_merge:
+        z_m, s_m = z_old, sdf_old
+    return z_new, z_m, s_m, inds, cdf
+
+
+def sample_pdf_from_cdf(bins, cdf, n_new):
+    bins, cdf = _f32(bins), _f32(cdf)
+    B, n = bins.shape
+    samples = torch.empty(B, n_new, dtype=torch.float32, device=bins.device)
+    inds = torch.empty(B, n_new, dtype=torch.int64, device=bins.device)
+    L.check(L.load().rnb_sample_pdf_from_cdf(L.ptr(bins), L.ptr(cdf), B, n, n_new, L.ptr(samples), L.ptr(inds),
+                                             L.stream_ptr()), "sample_pdf_from_cdf")
+    return samples, inds
+
+
+def final_merge(z_old, z_new, sample_dist):
+    B, n_old = z_old.shape
+    n_new = 0 if z_new is None else z_new.shape[1]
+    z = torch.empty(B, n_old + n_new, dtype=torch.float32, device=z_old.device)
+    mid = torch.empty_like(z)
+    L.check(L.load().rnb_final_merge(L.ptr(z_old), n_old, L.ptr(z_new), n_new, B, float(sample_dist), L.ptr(z), L.ptr(mid),
+                                     L.stream_ptr()), "final_merge")
+    return z, mid
+
+
+def composite_params(rays_o, rays_d, z, sdf, grad, albedo, lights, variance, cos_anneal_ratio, mode, sample_dist):
+    """mode: 0 = render_rnb (no relu), 1 = render_rnb_warmup (relu), 2 = plain colour (shade = 1)"""
+    B = z.shape[0]
+    assert z.shape[1] == 128, "the compositing kernel is specialised for 128 samples per ray"
+    p = L.Composite()
+    p.n_rays = B
+    p.rays_o, p.rays_d, p.z = L.ptr(rays_o), L.ptr(rays_d), L.ptr(z)
+    p.sdf, p.grad, p.albedo = L.ptr(sdf), L.ptr(grad), L.ptr(albedo)
+    nl = lights.shape[0]
+    lights = _f32(lights).reshape(nl, -1, 3)
+    p.lights, p.n_lights = L.ptr(lights), nl
+    p.light_stride_l = lights.shape[1] * 3
+    p.light_stride_ray = 3 if lights.shape[1] == B and B > 1 else (3 if lights.shape[1] == B else 0)
+    if lights.shape[1] not in (1, B):
+        raise RuntimeError(f"lights_dir must broadcast against [L,{B},1,3], got {tuple(lights.shape)}")
+    if lights.shape[1] == 1:
+        p.light_stride_ray = 0
+    p.variance = L.ptr(variance)
+    p.cos_anneal_ratio, p.warmup, p.sample_dist = float(cos_anneal_ratio), int(mode), float(sample_dist)
+    p._keep = (lights, rays_o, rays_d, z, sdf, grad, albedo, variance)   # the struct only holds raw pointers
+    return p
+
+
+def composite_fwd(p):
+    B, nl, dev = p.n_rays, p.n_lights, torch.device("cuda", torch.cuda.current_device())
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = dict(color=torch.empty(nl, B, 3, **f32), weights=torch.empty(B, 128, **f32), cdf=torch.empty(B, 128, **f32),
+               inside=torch.empty(B, 128, **f32), weight_sum=torch.empty(B, 1, **f32),
+               weight_max=torch.empty(B, 1, **f32), eik_part=torch.empty(B, 2, **f32))
+    p.color, p.weights, p.cdf, p.inside = (L.ptr(out[k]) for k in ("color", "weights", "cdf", "inside"))
+    p.weight_sum, p.weight_max, p.eik_part = (L.ptr(out[k]) for k in ("weight_sum", "weight_max", "eik_part"))
+    L.check(L.load().rnb_composite_fwd(C.byref(p), L.stream_ptr()), "composite_fwd")
+    return out
+
+
+def composite_bwd(p, d_color, d_weight_sum, d_eik, eik_den, want_albedo):
+    B, dev = p.n_rays, d_color.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    d_color = _f32(d_color)
+    d_ws = _f32(d_weight_sum).view(-1) if d_weight_sum is not None else None
+    out = dict(d_sdf=torch.empty(B * 128, **f32), d_grad=torch.empty(B * 128, 3, **f32),
+               d_albedo=torch.empty(B * 128, 3, **f32) if want_albedo else None, d_var_part=torch.empty(B, **f32))
+    p.d_color, p.d_weight_sum, p.d_eik, p.eik_den = L.ptr(d_color), L.ptr(d_ws), L.ptr(d_eik), L.ptr(eik_den)
+    p.d_sdf, p.d_grad, p.d_albedo, p.d_var_part = (L.ptr(out[k]) for k in ("d_sdf", "d_grad", "d_albedo", "d_var_part"))
+    L.check(L.load().rnb_composite_bwd(C.byref(p), L.stream_ptr()), "composite_bwd")
+    return out
+
+
 def stream_to_rowmajor(buf, n_pts, cols, dtype=torch.float16):
     """Decode a stream image [Npad/64][cols/8][64][8] into [n_pts, cols] (tests / debugging)."""
     t = buf.view(dtype).view(-1, cols // 8, 64, 8).permute(0, 2, 1, 3).reshape(-1, cols)

@@ -21,6 +21,27 @@ class Points(C.Structure):
                 ("bmin", C.c_float * 3), ("bmax", C.c_float * 3)]
 
 
+class Upsample(C.Structure):
+    """rnb_upsample_t"""
+    _fields_ = [("n_rays", C.c_int32), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("z_old", C.c_void_p),
+                ("sdf_old", C.c_void_p), ("n_old", C.c_int32), ("z_pending", C.c_void_p), ("sdf_pending", C.c_void_p),
+                ("n_merge", C.c_int32), ("z_merged", C.c_void_p), ("sdf_merged", C.c_void_p), ("inv_s", C.c_float),
+                ("n_new", C.c_int32), ("z_new", C.c_void_p), ("inds", C.c_void_p), ("cdf_out", C.c_void_p)]
+
+
+class Composite(C.Structure):
+    """rnb_composite_t"""
+    _fields_ = [("n_rays", C.c_int32), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("z", C.c_void_p),
+                ("sdf", C.c_void_p), ("grad", C.c_void_p), ("albedo", C.c_void_p), ("lights", C.c_void_p),
+                ("n_lights", C.c_int32), ("light_stride_l", C.c_int64), ("light_stride_ray", C.c_int64),
+                ("variance", C.c_void_p), ("cos_anneal_ratio", C.c_float), ("warmup", C.c_int32),
+                ("sample_dist", C.c_float), ("color", C.c_void_p), ("weights", C.c_void_p), ("cdf", C.c_void_p),
+                ("inside", C.c_void_p), ("weight_sum", C.c_void_p), ("weight_max", C.c_void_p),
+                ("eik_part", C.c_void_p), ("d_color", C.c_void_p), ("d_weight_sum", C.c_void_p), ("d_eik", C.c_void_p),
+                ("eik_den", C.c_void_p), ("d_sdf", C.c_void_p), ("d_grad", C.c_void_p), ("d_albedo", C.c_void_p),
+                ("d_var_part", C.c_void_p)]
+
+
 _lib = None
 
 _VP = C.c_void_p
@@ -35,6 +56,12 @@ _SIGNATURES = {
     "rnb_sdf_fwd": (C.c_int, [C.POINTER(Points), _VP, _VP, _VP, C.c_float, _VP]),
     "rnb_sdf_fwd_grad": (C.c_int, [C.POINTER(Points)] + [_VP] * 11),
     "rnb_sdf_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "rnb_coarse_z": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
+    "rnb_upsample_step": (C.c_int, [C.POINTER(Upsample), _VP]),
+    "rnb_sample_pdf_from_cdf": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),
+    "rnb_final_merge": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
+    "rnb_composite_fwd": (C.c_int, [C.POINTER(Composite), _VP]),
+    "rnb_composite_bwd": (C.c_int, [C.POINTER(Composite), _VP]),
     "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 10 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
 }
 
