@@ -1,0 +1,217 @@
+"""Autograd glue between the reference-shaped modules (models/fields.py, models/renderer.py) and the kernels.
+
+Host logic only: which kernel runs when, which buffers are kept for the backward, and how the cotangents flow
+(composite adjoint -> albedo net backward -> SDF double-backward).  Weight-norm stays in torch on parameter-sized
+tensors (W = g v/|v| via torch._weight_norm), so autograd turns the kernels' dW into (dg, dv) for free.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as K
+from . import lib as L
+
+FINE_SAMPLES = 128
+
+
+def _sdf_wb(sdf_module):
+    eff = sdf_module.effective_weights()
+    if len(eff) != 9:
+        raise RuntimeError("rnb_b200: the sm_100a SDF kernels are specialised for n_layers=8 (9 linears)")
+    if getattr(sdf_module, "multires", 6) != 6 or tuple(sdf_module.skip_in) != (4,) or float(sdf_module.scale) != 1.0:
+        raise RuntimeError("rnb_b200: SDF kernels support multires=6, skip_in=[4], scale=1.0 (the shipped confs)")
+    flat = []
+    for W, b in eff:
+        flat += [W, b]
+    return flat
+
+
+def _pack_sdf(flat, device):
+    pk = K.SdfPacked(device)
+    pk.pack(flat[0::2], flat[1::2])
+    return pk
+
+
+def packed_sdf_nograd(sdf_module):
+    """Packed operands for no_grad evaluation, cached until a parameter changes (version counters)."""
+    params = list(sdf_module.parameters())
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    cache = getattr(sdf_module, "_rnb_packed", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            flat = _sdf_wb(sdf_module)
+            L.require_cuda(flat[0], "SDFNetwork")
+            cache = (key, _pack_sdf(flat, flat[0].device))
+        sdf_module._rnb_packed = cache
+    return cache[1]
+
+
+# ------------------------------------------------------------------------------------------ module-level API
+def sdf_only(sdf_module, x):
+    """SDFNetwork.sdf under no_grad -> [N,1]"""
+    L.require_cuda(x, "SDFNetwork.sdf")
+    pk = packed_sdf_nograd(sdf_module)
+    return K.sdf_fwd(pk, K.points_explicit(x.reshape(-1, 3))).view(-1, 1)
+
+
+class _SdfEval(torch.autograd.Function):
+    """(out [N,257], grad [N,3]) of explicit points; differentiable w.r.t. the effective weights."""
+
+    @staticmethod
+    def forward(ctx, x, *flat):
+        pk = _pack_sdf(flat, x.device)
+        pts = K.points_explicit(x)
+        sdf, grad, full, streams = K.sdf_fwd_grad(pk, pts, want_full=True)
+        ctx.pk, ctx.pts, ctx.streams = pk, pts, streams
+        return full, grad
+
+    @staticmethod
+    def backward(ctx, d_full, d_grad):
+        n = ctx.pts.n_pts
+        dev = ctx.pk.wblob.device
+        if d_full is None:
+            d_full = torch.zeros(n, 257, device=dev)
+        if d_grad is None:
+            d_grad = torch.zeros(n, 3, device=dev)
+        d_sdf = d_full[:, 0].contiguous()
+        d_feat = d_full[:, 1:].contiguous()
+        dWs, dbs, _ = K.sdf_bwd(ctx.pk, ctx.pts, ctx.streams, d_sdf, d_grad, d_feat)
+        out = [None]
+        for W, b in zip(dWs, dbs):
+            out += [W, b]
+        return tuple(out)
+
+
+def sdf_forward(sdf_module, x, want_grad):
+    """-> (out [N,257], grad [N,3] or None)"""
+    L.require_cuda(x, "SDFNetwork.forward")
+    x2 = x.detach().reshape(-1, 3).float().contiguous()
+    flat = _sdf_wb(sdf_module)
+    needs = torch.is_grad_enabled() and any(t.requires_grad for t in flat)
+    if needs:
+        full, grad = _SdfEval.apply(x2, *flat)
+    else:
+        with torch.no_grad():
+            pk = packed_sdf_nograd(sdf_module)
+            _, grad, full, _ = K.sdf_fwd_grad(pk, K.points_explicit(x2), want_full=True)
+    return full, (grad if want_grad else None)
+
+
+def albedo_forward(color_module, points, normals, view_dirs, feature_vectors):
+    raise NotImplementedError("rnb_b200: stand-alone RenderingNetwork.forward lands with the albedo kernels")
+
+
+def nerf_forward(nerf_module, input_pts, input_views):
+    raise NotImplementedError("rnb_b200: the NeRF++ background field is not built yet (all shipped confs set n_outside=0)")
+
+
+# ------------------------------------------------------------------------------------------ sampling
+@torch.no_grad()
+def hierarchical_sample(sdf_module, rays_o, rays_d, near, far, t_rand, n_samples, n_importance, up_sample_steps):
+    """The no_grad block of render*/render_rnb* (reference models/renderer.py:829-880): -> (z_vals, mid_z_vals)."""
+    pk = packed_sdf_nograd(sdf_module)
+    o = rays_o.detach().float().contiguous()
+    d = rays_d.detach().float().contiguous()
+    B = o.shape[0]
+    z = K.coarse_z(near, far, t_rand, n_samples)
+    last = None
+    if n_importance > 0:
+        sdf = K.sdf_fwd(pk, K.points_rays(o, d, z)).view(B, n_samples)
+        n_new = n_importance // up_sample_steps
+        pend_z = pend_s = None
+        for i in range(up_sample_steps):
+            z_new, z, sdf, _, _ = K.upsample_step(o, d, z, sdf, 64 * 2 ** i, n_new, pend_z, pend_s)
+            if i + 1 < up_sample_steps:
+                pend_z = z_new
+                pend_s = K.sdf_fwd(pk, K.points_rays(o, d, z_new)).view(B, n_new)
+            else:
+                last = z_new
+    return K.final_merge(z, last, 2.0 / n_samples)
+
+
+# ------------------------------------------------------------------------------------------ fine pass
+class _RnbFine(torch.autograd.Function):
+    """render_core_mvps + RNb shading (reference models/renderer.py:466-554, 904-918, 1008-1017) as one node.
+
+    inputs : meta dict, rays_o, rays_d, z_vals, mid_z, lights, variance, 18 SDF tensors (W_l, b_l), [6 colour tensors]
+    outputs: color [L,B,3], weight_sum [B,1], gradient_error [] (differentiable);
+             weights, cdf, inside_sphere, weight_max, gradients [B,128,3], sdf [B*128,1] (not differentiable)
+    """
+
+    @staticmethod
+    def forward(ctx, meta, rays_o, rays_d, z_vals, mid_z, lights, variance, *wb):
+        dev = z_vals.device
+        B = z_vals.shape[0]
+        sdf_flat = wb[:18]
+        col_flat = wb[18:]
+        use_albedo = meta["use_albedo"]
+        pk = _pack_sdf(sdf_flat, dev)
+        pts = K.points_rays(rays_o, rays_d, mid_z)
+        sdf, grad, _, streams = K.sdf_fwd_grad(pk, pts)
+        albedo = None
+        if use_albedo:
+            from . import albedo as A
+            actx = A.forward(col_flat, pts, grad, streams)
+            albedo = actx.albedo
+            ctx.actx = actx
+        var = variance.detach().float().reshape(1).contiguous()
+        cp = K.composite_params(rays_o, rays_d, z_vals, sdf, grad, albedo, lights, var, meta["cos_anneal_ratio"],
+                                meta["mode"], meta["sample_dist"])
+        out = K.composite_fwd(cp)
+        eik = out["eik_part"].sum(0)
+        grad_err = eik[0] / (eik[1] + 1e-5)
+        ctx.pk, ctx.pts, ctx.streams, ctx.cp = pk, pts, streams, cp
+        ctx.eik_den = eik[1:2].contiguous()
+        ctx.use_albedo = use_albedo
+        ctx.n_col = len(col_flat)
+        gradients = grad.view(B, FINE_SAMPLES, 3)
+        ctx.mark_non_differentiable(out["weights"], out["cdf"], out["inside"], out["weight_max"], gradients, sdf)
+        sampled_albedo = albedo.view(B, FINE_SAMPLES, 3) if albedo is not None else None
+        if sampled_albedo is not None:
+            ctx.mark_non_differentiable(sampled_albedo)
+        return (out["color"], out["weight_sum"], grad_err, out["weights"], out["cdf"], out["inside"], out["weight_max"],
+                gradients, sdf, sampled_albedo)
+
+    @staticmethod
+    def backward(ctx, d_color, d_wsum, d_eik, *unused):
+        cp = ctx.cp
+        dev = ctx.pk.wblob.device
+        B, nl = cp.n_rays, cp.n_lights
+        if d_color is None:
+            d_color = torch.zeros(nl, B, 3, device=dev)
+        if d_eik is None:
+            d_eik = torch.zeros((), device=dev)
+        d_eik = d_eik.detach().float().reshape(1).contiguous()
+        bw = K.composite_bwd(cp, d_color, d_wsum, d_eik, ctx.eik_den, ctx.use_albedo)
+        d_grad = bw["d_grad"]
+        d_feat = None
+        col_grads = [None] * ctx.n_col
+        if ctx.use_albedo:
+            from . import albedo as A
+            d_normal, d_feat, col_grads = A.backward(ctx.actx, bw["d_albedo"])
+            d_grad = d_grad + d_normal
+        dWs, dbs, _ = K.sdf_bwd(ctx.pk, ctx.pts, ctx.streams, bw["d_sdf"], d_grad, d_feat)
+        d_var = bw["d_var_part"].sum().reshape(())
+        grads = [None, None, None, None, None, None, d_var]
+        for W, b in zip(dWs, dbs):
+            grads += [W, b]
+        grads += list(col_grads)
+        return tuple(grads)
+
+
+def rnb_fine(sdf_module, color_module, variance, rays_o, rays_d, z_vals, mid_z, lights, cos_anneal_ratio, mode,
+             use_albedo, sample_dist):
+    """mode 0: render_rnb, 1: render_rnb_warmup, 2: plain colour (render)."""
+    if z_vals.shape[1] != FINE_SAMPLES:
+        raise RuntimeError(f"rnb_b200: the fine pass is specialised for n_samples + n_importance = {FINE_SAMPLES} "
+                           f"(got {z_vals.shape[1]})")
+    flat = _sdf_wb(sdf_module)
+    col = []
+    if use_albedo:
+        for W, b in color_module.effective_weights():
+            col += [W, b]
+    meta = dict(use_albedo=use_albedo, cos_anneal_ratio=float(cos_anneal_ratio), mode=int(mode),
+                sample_dist=float(sample_dist))
+    o = rays_o.detach().float().contiguous()
+    d = rays_d.detach().float().contiguous()
+    return _RnbFine.apply(meta, o, d, z_vals, mid_z, lights.detach(), variance, *flat, *col)
