@@ -144,6 +144,26 @@ RNB_API int rnb_final_merge(const float* z_old, int n_old, const float* z_new, i
 RNB_API int rnb_composite_fwd(const rnb_composite_t* p, void* stream);
 RNB_API int rnb_composite_bwd(const rnb_composite_t* p, void* stream);
 
+/* ---- albedo network (reference RenderingNetwork mode 'no_view_dir', models/fields.py:131-215) ------------- */
+RNB_API size_t rnb_albedo_wblob_bytes(void);
+RNB_API size_t rnb_albedo_aux_floats(void);
+/* effective fp32 weights: W0 [256,310], W1 [256,256], W2 [3,256] and biases -> packed operands */
+RNB_API int rnb_albedo_pack(const float* W0, const float* b0, const float* W1, const float* b1, const float* W2, const float* b2,
+                    void* wblob, float* aux, void* stream);
+/* albedo[n,3] = sigmoid(MLP([PE4(points), PE4(normals), features])); the view directions of the reference call
+ * (models/renderer.py:501) are embedded and then unused in mode 'no_view_dir' (models/fields.py:179-192), so they
+ * are not an argument.  st_feat: feature stream of rnb_sdf_fwd_grad; st_pe [Npad x 64], st_h0/st_h1 [Npad x 256]
+ * are written for the backward. */
+RNB_API int rnb_albedo_fwd(const rnb_points_t* pts, const float* normals, const void* st_feat, const void* wblob, const float* aux,
+                   float* albedo, void* st_pe, void* st_h0, void* st_h1, void* stream);
+RNB_API size_t rnb_albedo_bwd_scratch_bytes(int64_t n_pts);
+/* VJP: d_albedo [n,3] -> d_normal [n,3], d_feat [n,256] (fp32 row-major) and the effective-weight gradients
+ * dW0 [256,310], db0 [256], dW1 [256,256], db1 [256], dW2 [3,256], db2 [3] (overwritten). */
+RNB_API int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* albedo, const float* d_albedo,
+                   const void* st_feat, const void* st_pe, const void* st_h0, const void* st_h1, const void* wblob,
+                   const float* aux, void* scratch, float* d_normal, float* d_feat, float* dW0, float* db0, float* dW1,
+                   float* db1, float* dW2, float* db2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

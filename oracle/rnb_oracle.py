@@ -264,9 +264,13 @@ def color_forward(Ws, bs, points, normals, feat, multires_view=4, keep=False):
     return out
 
 
-def color_backward(Ws, bs, points, normals, feat, d_out, multires_view=4):
+def color_backward(Ws, bs, points, normals, feat, d_out, multires_view=4, relu_masks=None):
     """Returns dWs, dbs, d_normals [N,3], d_feat [N,F].  (points carry no gradient:
-    sample positions are detached, models/renderer.py:175, 862.)"""
+    sample positions are detached, models/renderer.py:175, 862.)
+    relu_masks (optional, list per hidden layer): use these ReLU activity masks instead of the oracle's own --
+    a reduced-precision forward flips the sign of the few pre-activations that sit within its rounding error of
+    zero, and a flipped unit changes that point's cotangent by 100 %; tests that check the backward ARITHMETIC
+    feed the kernel's masks."""
     out, ins, zs = color_forward(Ws, bs, points, normals, feat, multires_view, keep=True)
     n_lin = len(Ws)
     dWs = [None] * n_lin
@@ -277,7 +281,8 @@ def color_backward(Ws, bs, points, normals, feat, d_out, multires_view=4):
         dbs[l] = zbar.sum(0)
         hbar = zbar @ Ws[l]
         if l > 0:
-            zbar = hbar * (zs[l - 1] > 0)
+            mask = (zs[l - 1] > 0) if relu_masks is None else relu_masks[l - 1]
+            zbar = hbar * mask
     d_pe = 3 * (1 + 2 * multires_view)
     d_ne = hbar[:, d_pe:2 * d_pe]
     d_feat = hbar[:, 2 * d_pe:]

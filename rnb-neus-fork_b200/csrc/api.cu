@@ -3,9 +3,11 @@
 #include "sdf_params.h"
 #include "dw_params.h"
 #include "render_params.h"
+#include "albedo_params.h"
 #include <algorithm>
 
 namespace rnb {
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 cudaError_t launch_sdf_pack(const float* const* W, const float* const* b, uint8_t* blob, float* aux, cudaStream_t st);
 cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_sdf_fwd_grad(const SdfFwdGradParams& P, int sm_count, cudaStream_t st);
@@ -24,13 +26,39 @@ cudaError_t launch_sample_pdf_from_cdf(const float* bins, const float* cdf, int 
 cudaError_t launch_final_merge(const float* z_old, int n_old, const float* z_new, int n_new, int n_rays, float sample_dist,
                                float* z_out, float* mid_out, cudaStream_t st);
 cudaError_t launch_composite(const CompositeParams& P, bool bwd, cudaStream_t st);
+cudaError_t launch_albedo_pack(const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                               const float* b2, uint8_t* blob, float* aux, cudaStream_t st);
+cudaError_t launch_albedo_fwd(const AlbedoFwdParams& P, int sm_count, cudaStream_t st);
+cudaError_t launch_albedo_bwd(const AlbedoBwdParams& P, int sm_count, cudaStream_t st);
+
+struct AlbedoBwdScratch {
+    size_t absmax, dz2, dz1, dz0, dw_part, cs_part, total;
+    int dw_splits, cs_splits;
+};
+static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
+    AlbedoBwdScratch L;
+    const size_t s256 = rnb_stream_bytes(n_pts, 256);
+    const int64_t n_pad = rnb_padded_points(n_pts);
+    const int n_sub = (int)(n_pad / 64);
+    L.dw_splits = std::max(1, std::min(n_sub, 96));
+    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 32));
+    size_t o = 0;
+    L.absmax = o; o += 256;
+    L.dz2 = o; o += align_up((size_t)3 * n_pad * 4, 256);
+    L.dz1 = o; o += s256;
+    L.dz0 = o; o += s256;
+    o = align_up(o, 256);
+    L.dw_part = o; o += (size_t)L.dw_splits * 256 * (256 + 256 + 64) * 4;
+    L.cs_part = o; o += (size_t)L.cs_splits * 256 * 5 * 4;
+    L.total = align_up(o, 256);
+    return L;
+}
 
 // scratch layout of rnb_sdf_bwd
 struct SdfBwdScratch {
     size_t absmax, uin0, uin, z2, zbar, dfeat, dw_part, cs_part, total;
     int dw_splits, cs_splits;
 };
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     SdfBwdScratch L;
     const size_t s256 = rnb_stream_bytes(n_pts, 256), s64 = rnb_stream_bytes(n_pts, 64);
@@ -70,7 +98,8 @@ static SdfPointSource to_src(const rnb_points_t* p) {
     return s;
 }
 
-static void add_step(ChainTable& t, uint32_t off, int n, int k) {
+static void add_step(ChainTable& t, uint32_t off, int n, int k, int accumulate = 0) {
+    t.steps[t.n_steps].accumulate = (uint32_t)accumulate;
     t.steps[t.n_steps].w_off = off;
     t.steps[t.n_steps].n = (uint16_t)n;
     t.steps[t.n_steps].k = (uint16_t)k;
@@ -249,5 +278,105 @@ int rnb_final_merge(const float* z_old, int n_old, const float* z_new, int n_new
 }
 int rnb_composite_fwd(const rnb_composite_t* p, void* stream) { return (int)launch_composite(*p, false, (cudaStream_t)stream); }
 int rnb_composite_bwd(const rnb_composite_t* p, void* stream) { return (int)launch_composite(*p, true, (cudaStream_t)stream); }
+
+
+size_t rnb_albedo_wblob_bytes(void) { return ALBW_BYTES; }
+size_t rnb_albedo_aux_floats(void) { return ALBX_FLOATS; }
+int rnb_albedo_pack(const float* W0, const float* b0, const float* W1, const float* b1, const float* W2, const float* b2,
+                    void* wblob, float* aux, void* stream) {
+    return (int)launch_albedo_pack(W0, b0, W1, b1, W2, b2, (uint8_t*)wblob, aux, (cudaStream_t)stream);
+}
+
+int rnb_albedo_fwd(const rnb_points_t* pts, const float* normals, const void* st_feat, const void* wblob, const float* aux,
+                   float* albedo, void* st_pe, void* st_h0, void* st_h1, void* stream) {
+    AlbedoFwdParams P{};
+    P.src = to_src(pts);
+    P.n_tiles = n_tiles(pts->n_pts);
+    P.wblob = (const uint8_t*)wblob;
+    P.aux = aux;
+    add_step(P.tab, ALBW_F0A, 256, 256);
+    add_step(P.tab, ALBW_F0B, 256, 64, 1);
+    add_step(P.tab, ALBW_F1, 256, 256);
+    P.normals = normals; P.st_feat = (const uint8_t*)st_feat; P.albedo = albedo;
+    P.st_pe = (uint8_t*)st_pe; P.st_h0 = (uint8_t*)st_h0; P.st_h1 = (uint8_t*)st_h1;
+    return (int)launch_albedo_fwd(P, sm_count(), (cudaStream_t)stream);
+}
+
+size_t rnb_albedo_bwd_scratch_bytes(int64_t n_pts) { return albedo_bwd_scratch(n_pts).total; }
+
+int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* albedo, const float* d_albedo,
+                   const void* st_feat, const void* st_pe, const void* st_h0, const void* st_h1, const void* wblob,
+                   const float* aux, void* scratch, float* d_normal, float* d_feat, float* dW0, float* db0, float* dW1,
+                   float* db1, float* dW2, float* db2, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = pts->n_pts;
+    if (n <= 0) return 0;
+    const AlbedoBwdScratch L = albedo_bwd_scratch(n);
+    uint8_t* sc = (uint8_t*)scratch;
+    float* absmax = (float*)(sc + L.absmax);
+    const int64_t n_pad = rnb_padded_points(n);
+    cudaError_t e = launch_absmax(d_albedo, 3 * n, nullptr, 0, nullptr, 0, absmax, st);
+    if (e != cudaSuccess) return (int)e;
+    AlbedoBwdParams P{};
+    P.src = to_src(pts);
+    P.n_tiles = n_tiles(n);
+    P.wblob = (const uint8_t*)wblob;
+    P.aux = aux;
+    add_step(P.tab, ALBW_T1, 256, 256);
+    add_step(P.tab, ALBW_T0A, 256, 256);
+    add_step(P.tab, ALBW_T0B, 64, 256);
+    P.normals = normals; P.albedo = albedo; P.d_albedo = d_albedo; P.cot_absmax = absmax;
+    P.st_h0 = (const uint8_t*)st_h0; P.st_h1 = (const uint8_t*)st_h1;
+    P.n_pad = n_pad;
+    P.dz2 = (float*)(sc + L.dz2);
+    P.st_dz1 = sc + L.dz1; P.st_dz0 = sc + L.dz0;
+    P.d_feat = d_feat; P.d_normal = d_normal;
+    e = launch_albedo_bwd(P, sm_count(), st);
+    if (e != cudaSuccess) return (int)e;
+    const int n_sub = (int)(n_pad / 64);
+    DwParams D{};
+    D.n_sub = n_sub;
+    ReduceParams R{};
+    R.cot_absmax = absmax;
+    float* part = (float*)(sc + L.dw_part);
+    auto add_dw = [&](const uint8_t* a, const uint8_t* b, int b_chunks, int nw, float* dst, int pitch, int col0, int out_cols) {
+        DwJob& j = D.jobs[D.n_jobs++];
+        j.n_pairs = 1; j.a[0] = a; j.b[0] = b; j.b_chunks[0] = b_chunks; j.b_chunk0 = 0; j.nw = nw; j.partial = part;
+        ReduceJob& r = R.jobs[R.n_jobs++];
+        r.partial = part; r.splits = L.dw_splits; r.rows = 256; r.nw = nw;
+        r.dst = dst; r.dst_pitch = pitch; r.dst_row0 = 0; r.dst_col0 = col0; r.out_rows = 256; r.out_cols = out_cols;
+        r.factor = 1.f; r.use_cot_scale = 1;
+        part += (size_t)L.dw_splits * 256 * nw;
+    };
+    add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256);
+    add_dw(sc + L.dz0, (const uint8_t*)st_feat, 32, 256, dW0, 310, 54, 256);
+    add_dw(sc + L.dz0, (const uint8_t*)st_pe, 8, 64, dW0, 310, 0, 54);
+    e = launch_dw_gemm(D, L.dw_splits, st);
+    if (e != cudaSuccess) return (int)e;
+    ColsumParams C{};
+    C.n_sub = n_sub;
+    C.n_pts = n_pad;
+    float* cpart = (float*)(sc + L.cs_part);
+    auto add_cs = [&](const uint8_t* stream, const float* wgt, float* dst, int use_scale) {
+        ColsumJob& j = C.jobs[C.n_jobs++];
+        j.stream = stream; j.chunks = 32; j.row_weight = wgt; j.partial = cpart;
+        ReduceJob& r = R.jobs[R.n_jobs++];
+        r.partial = cpart; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
+        r.dst = dst; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = use_scale;
+        cpart += (size_t)L.cs_splits * 256;
+    };
+    add_cs(sc + L.dz1, nullptr, db1, 1);
+    add_cs(sc + L.dz0, nullptr, db0, 1);
+    for (int k = 0; k < 3; ++k) add_cs((const uint8_t*)st_h1, P.dz2 + (size_t)k * n_pad, dW2 + k * 256, 0);
+    e = launch_colsum(C, L.cs_splits, st);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_reduce(R, st);
+    if (e != cudaSuccess) return (int)e;
+    for (int k = 0; k < 3; ++k) {
+        e = launch_sum(P.dz2 + (size_t)k * n_pad, n_pad, db2 + k, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
 
 }  // extern "C"

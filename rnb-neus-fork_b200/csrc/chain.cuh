@@ -25,6 +25,7 @@ struct ChainStep {
     uint32_t w_off;   // byte offset of the packed [n x k] fp16 weight image in the blob
     uint16_t n;       // UMMA N (rows of the weight image), multiple of 16, <= 256
     uint16_t k;       // K, multiple of 32
+    uint32_t accumulate;   // 1: add onto the accumulator left by the previous step (split-K over two A operands)
 };
 struct ChainTable {
     int n_steps;
@@ -121,7 +122,7 @@ __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& 
                 for (int j = 0; j < 2; ++j) {
                     const uint64_t ad = umma_desc(a_base + (uint32_t)(ks * 2 + j) * (2 * TILE_M * 16), TILE_M * 16, 128);
                     const uint64_t bd = umma_desc(ring_base + slot * STAGE_BYTES + (uint32_t)j * (2 * n * 16), n * 16, 128);
-                    umma_f16(tmem, ad, bd, idesc, (ks | j) != 0);
+                    umma_f16(tmem, ad, bd, idesc, ((ks | j) != 0) || tab.steps[st].accumulate);
                 }
                 umma_commit(&s.empty[slot]);
             }

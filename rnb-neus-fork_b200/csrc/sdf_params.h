@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 #include "chain.cuh"
+#include "points.cuh"
 
 namespace rnb {
 
@@ -21,19 +22,6 @@ __host__ __device__ constexpr uint32_t sdfw_tr(int l) { return l == 0 ? SDFW_T0 
 constexpr int AUX_W8ROW = 9 * 256;
 constexpr int AUX_B8_0 = AUX_W8ROW + 256;
 constexpr int AUX_FLOATS = AUX_B8_0 + 4;
-
-// where the points of a launch come from
-struct SdfPointSource {
-    int64_t n_pts;
-    const float* x;            // [n_pts,3]                          (explicit points)
-    const float* rays_o;       // [B,3]  point = o + d*z             (ray samples)
-    const float* rays_d;       // [B,3]
-    const float* z;            // [B*n_per_ray]
-    int n_per_ray;
-    int grid_res;              // > 0: points of the R^3 lattice, x index offset by slab_x0
-    int slab_x0;
-    float bmin[3], bmax[3];
-};
 
 struct SdfFwdParams {
     SdfPointSource src;

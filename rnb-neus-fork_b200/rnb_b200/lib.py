@@ -56,6 +56,12 @@ _SIGNATURES = {
     "rnb_sdf_fwd": (C.c_int, [C.POINTER(Points), _VP, _VP, _VP, C.c_float, _VP]),
     "rnb_sdf_fwd_grad": (C.c_int, [C.POINTER(Points)] + [_VP] * 11),
     "rnb_sdf_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "rnb_albedo_wblob_bytes": (C.c_size_t, []),
+    "rnb_albedo_aux_floats": (C.c_size_t, []),
+    "rnb_albedo_pack": (C.c_int, [_VP] * 9),
+    "rnb_albedo_fwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 9),
+    "rnb_albedo_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "rnb_albedo_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 19),
     "rnb_coarse_z": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
     "rnb_upsample_step": (C.c_int, [C.POINTER(Upsample), _VP]),
     "rnb_sample_pdf_from_cdf": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),

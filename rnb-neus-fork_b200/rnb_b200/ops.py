@@ -165,10 +165,11 @@ class _RnbFine(torch.autograd.Function):
         ctx.use_albedo = use_albedo
         ctx.n_col = len(col_flat)
         gradients = grad.view(B, FINE_SAMPLES, 3)
-        ctx.mark_non_differentiable(out["weights"], out["cdf"], out["inside"], out["weight_max"], gradients, sdf)
         sampled_albedo = albedo.view(B, FINE_SAMPLES, 3) if albedo is not None else None
+        nd = [out["weights"], out["cdf"], out["inside"], out["weight_max"], gradients, sdf]
         if sampled_albedo is not None:
-            ctx.mark_non_differentiable(sampled_albedo)
+            nd.append(sampled_albedo)
+        ctx.mark_non_differentiable(*nd)
         return (out["color"], out["weight_sum"], grad_err, out["weights"], out["cdf"], out["inside"], out["weight_max"],
                 gradients, sdf, sampled_albedo)
 

@@ -78,3 +78,50 @@ def test_sdf_backward(perturb, n):
             assert np.isfinite(got).all(), nm
             assert cosine(got, ref) > 0.999, (nm, cosine(got, ref))
             assert rel_l2(got, ref) < 1e-2, (nm, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+def test_albedo_fwd_bwd(perturb):
+    """Albedo net on the SDF kernel's own feature stream, against the oracle (colour tolerance 1e-3; grads 1e-2)."""
+    from conftest import cosine
+    from rnb_b200 import kernels as K, albedo as A
+    n = 3000
+    _, sdf, _, col = build_nets(perturb)
+    pk = packed_for(sdf)
+    g = torch.Generator().manual_seed(7)
+    x = ((torch.rand(n, 3, generator=g) - 0.5) * 2.0).cuda()
+    pts = K.points_explicit(x)
+    _, grad, full, st = K.sdf_fwd_grad(pk, pts, want_full=True)
+    flat = []
+    for W, b in col.effective_weights():
+        flat += [W, b]
+    ctx = A.forward(flat, pts, grad, st)
+    torch.cuda.synchronize()
+    cs = np_state(col)
+    cWs = [O.weight_norm_fold(cs[f"lin{l}.weight_g"], cs[f"lin{l}.weight_v"]) for l in range(3)]
+    cbs = [cs[f"lin{l}.bias"] for l in range(3)]
+    feat16 = K.stream_to_rowmajor(st.feat, n, 256).float().cpu().numpy()     # the fp16 features the kernel consumed
+    ref = O.color_forward(cWs, cbs, x.cpu().numpy(), grad.cpu().numpy(), feat16)
+    assert rel_l2(ctx.albedo.cpu().numpy(), ref) < 1e-3
+    ref_full = O.color_forward(cWs, cbs, x.cpu().numpy(), grad.cpu().numpy(), full[:, 1:].cpu().numpy())
+    assert rel_l2(ctx.albedo.cpu().numpy(), ref_full) < 1e-3
+    d_alb = (torch.randn(n, 3, generator=g) * 1e-4 * torch.rand(n, 1, generator=g) ** 3).cuda()
+    d_normal, d_feat, grads = A.backward(ctx, d_alb)
+    torch.cuda.synchronize()
+    # (i) backward arithmetic, with the kernel's own ReLU masks (see oracle.color_backward)
+    masks = [K.stream_to_rowmajor(ctx.st_h0, n, 256).float().cpu().numpy() > 0,
+             K.stream_to_rowmajor(ctx.st_h1, n, 256).float().cpu().numpy() > 0]
+    mW, mb, rn, rf = O.color_backward(cWs, cbs, x.cpu().numpy(), grad.cpu().numpy(), feat16, d_alb.cpu().numpy(),
+                                      relu_masks=masks)
+    assert rel_l2(d_normal.cpu().numpy(), rn) < 1e-2, rel_l2(d_normal.cpu().numpy(), rn)
+    assert rel_l2(d_feat.cpu().numpy(), rf) < 1e-2, rel_l2(d_feat.cpu().numpy(), rf)
+    # (ii) against the exact oracle: per-point cotangents carry the mask-flip noise (a few 1e-4 of the units),
+    # parameter gradients (sums over points) must still meet the gradient criterion
+    rW, rb, rn2, rf2 = O.color_backward(cWs, cbs, x.cpu().numpy(), grad.cpu().numpy(), feat16, d_alb.cpu().numpy())
+    assert cosine(d_normal.cpu().numpy(), rn2) > 0.999 and cosine(d_feat.cpu().numpy(), rf2) > 0.999
+    for l in range(3):
+        for nm, got, want, exact in ((f"dW{l}", grads[2 * l], mW[l], rW[l]), (f"db{l}", grads[2 * l + 1], mb[l], rb[l])):
+            got = got.cpu().numpy()
+            assert rel_l2(got, want) < 1e-2, (nm, rel_l2(got, want))            # arithmetic, same masks
+            assert cosine(got, exact) > 0.999, (nm, cosine(got, exact))         # exact oracle
+            assert rel_l2(got, exact) < 3e-2, (nm, rel_l2(got, exact))          # 3000 points, sparse cotangents
