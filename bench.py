@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the RNb-NeuS hot path on B200 (contract: see the task prompt / DESIGN.md 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dp8192|b512_noalbedo|grid512] [--impl reference]
+
+A "step" is one pass of the train_rnb hot path over one synthetic ray batch: render_rnb_warmup forward + the loss of
+exp_runner.py:241-256 + backward (eikonal double-backward included) + the gradient all-reduce when N > 1.
+Default workload (BASELINE.json configs[3]): wmask_rnb.conf with the albedo network, 8192 rays per GPU, weak scaling.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "rnb-neus-fork_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+# algorithmic FLOPs
+FLOP_SDF_ONLY = 918016
+FLOP_FWD_FULL = 1049088
+FLOP_DX = 917504
+FLOP_BWD_DATA = 2 * (458752 + 514560)
+FLOP_BWD_DW = 2 * (458752 + 524544)
+FLOP_ALB_FWD = 291328
+FLOP_ALB_BWD = 873984 - 291328
+FLOP_PER_RAY = {True: 967303168, False: 855433216}          # with / without the albedo net
+
+WORKLOADS = {
+    "dp8192": dict(rays=8192, no_albedo=False, desc="wmask_rnb.conf train_rnb (render_rnb_warmup fwd + loss + bwd + eikonal), "
+                   "8192 rays/GPU, 64+64 samples, 3 lights, albedo net on"),
+    "b512_noalbedo": dict(rays=512, no_albedo=True, desc="wmask_rnb_noalbedo.conf train_rnb --no_albedo, 512 rays, 64+64 samples"),
+    "b512": dict(rays=512, no_albedo=False, desc="wmask_rnb.conf train_rnb, 512 rays, 64+64 samples"),
+    "grid512": dict(rays=0, no_albedo=True, desc="validate_mesh extract_fields, 512^3 SDF lattice sharded in x-slabs"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def loss_fn(out, true_rgb, mask, igr_weight=0.1, mask_weight=0.1):
+    """reference exp_runner.py:241-256"""
+    mask_sum = mask.sum() + 1e-5
+    err = ((out["color_fine"] - true_rgb) * mask[None, :, :]).reshape(-1, 3)
+    color_loss = F.l1_loss(err, torch.zeros_like(err), reduction="sum") / (mask_sum * true_rgb.shape[0])
+    mask_loss = F.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), mask)
+    return color_loss + out["gradient_error"] * igr_weight + mask_loss * mask_weight
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for i, nme in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].strip().lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def build(device, geometric=True):
+    from models.fields import NeRF, SDFNetwork, SingleVarianceNetwork, RenderingNetwork
+    from models.renderer import NeuSRenderer
+    from rnb_b200 import synth
+    torch.manual_seed(0)
+    conf = synth.WMASK_CONF
+    nerf = NeRF(**conf["nerf"])
+    sdf = SDFNetwork(**conf["sdf_network"])
+    var = SingleVarianceNetwork(**conf["variance_network"])
+    col = RenderingNetwork(**conf["rendering_network"])
+    for m in (nerf, sdf, var, col):
+        m.to(device)
+    renderer = NeuSRenderer(nerf, sdf, var, col, **conf["neus_renderer"])
+    renderer.color_depth = 3
+    return renderer, sdf, var, col
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, wl):
+    """The path's CPU implementation on the box's host cores: the unmodified reference when /root/reference is
+    present (build container), else the numpy oracle port.  A bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_loader
+    from rnb_b200 import synth
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    if args.workload == "grid512":
+        n_q = 32 ** 3
+        sample = f"{n_q} lattice queries (one 32^3 block) per step"
+    else:
+        n_rays = 32
+        sample = f"{n_rays} rays of the workload per step (fwd + loss + bwd)"
+    kind = "reference" if ref_loader.available() else "port"
+    times = []
+    if kind == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        from oracle.gen_golden import build_reference_nets, loss_fn as ref_loss
+        ref, nerf, sdf, var, col = build_reference_nets(False)
+        renderer = ref.renderer.NeuSRenderer(nerf, sdf, var, col, **synth.WMASK_CONF["neus_renderer"])
+        renderer.color_depth = 3
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            if args.workload == "grid512":
+                with torch.no_grad():
+                    ref.renderer.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), 32, lambda p: -sdf.sdf(p))
+            else:
+                b = synth.make_batch(n_rays, 3, True, 1, view=it)
+                for m in (sdf, var, col):
+                    m.zero_grad()
+                out = renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
+                                                 cos_anneal_ratio=1.0, no_albedo=wl["no_albedo"])
+                ref_loss(out, b["true_rgb"], b["mask"], 0.1, 0.1, 3)[0].backward()
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        from oracle import rnb_oracle as O
+        renderer, sdf, var, col = build("cpu")
+        sd = lambda m: {k: v.detach().double().numpy() for k, v in m.state_dict().items()}
+        sdf_sd, col_sd = sd(sdf), sd(col)
+        Ws, bs = O.sdf_effective(sdf_sd)
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            if args.workload == "grid512":
+                O.extract_fields(Ws, bs, [-1.01] * 3, [1.01] * 3, 32)
+            else:
+                b = {k: v.numpy() for k, v in synth.make_batch(n_rays, 3, True, 1, view=it).items()}
+                ret, cache = O.render_rnb(sdf_sd, col_sd, 0.3, b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
+                                          b["t_rand"], 1.0, True, wl["no_albedo"])
+                O.train_step_grads(ret, cache, b["true_rgb"], b["mask"])
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    units = n_q if args.workload == "grid512" else n_rays
+    val = units / sec
+    unit = "SDF queries/s" if args.workload == "grid512" else "rays/s"
+    line = dict(impl="reference", metric=metric_name(args.workload), value=val, unit=unit, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32" if kind == "reference" else "f64", data="synthetic",
+                config=dict(workload=wl["desc"], sample=sample),
+                cpu_baseline=dict(value=val, unit=unit, cores=cores, kind=kind, sample=sample),
+                e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def metric_name(workload):
+    return "mesh SDF queries/s" if workload == "grid512" else "train rays/s (fwd+bwd+eikonal)"
+
+
+def cpu_baseline(args, wl):
+    """Oracle port (or the reference, when present) on the host cores, bounded sample; rank 0, N = 1 only."""
+    from oracle import ref_loader
+    ns = argparse.Namespace(**vars(args))
+    ns.steps, ns.warmup = (2, 1)
+    import io
+    import contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        run_reference(ns, wl)
+    try:
+        return json.loads(buf.getvalue().strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as e:  # noqa: BLE001
+        return dict(value=None, unit="rays/s", cores=os.cpu_count(), kind="port", sample=f"failed: {e}")
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dp8192", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from rnb_b200 import synth, lib as L, grid
+    from rnb_b200.parallel import FlatGradAllReducer
+
+    renderer, sdf, var, col = build(dev)
+    pk = peaks()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    if args.workload == "grid512":
+        R = 512
+        x0, x1 = grid.slab_bounds(R, rank, world)
+        out = torch.empty(x1 - x0, R, R, dtype=torch.float32, device=dev)
+        bmin, bmax = [-1.01] * 3, [1.01] * 3
+        host = torch.empty(x1 - x0, R, R, dtype=torch.float32).pin_memory()
+        step = lambda i: grid.sdf_slab(sdf, bmin, bmax, R, x0, x1, out=out)
+        for i in range(args.warmup):
+            step(i)
+        clk = ClockSampler(local)
+        L.profile_enable(True)
+        n0 = L.launch_count()
+        ms = timed(step, args.steps)
+        launches = L.launch_count() - n0
+        prof = L.profile_collect()
+        L.profile_enable(False)
+        clocks = clk.stop()
+
+        def e2e_step(i):
+            step(i)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        ms_e2e = timed(e2e_step, max(2, args.steps // 4))
+        units = R ** 3
+        kname, flop_unit, units_launch = "sdf_fwd", FLOP_SDF_ONLY, (x1 - x0) * R * R
+        h2d, d2h = 0, (x1 - x0) * R * R * 4
+        unit = "SDF queries/s"
+    else:
+        B = wl["rays"]
+        no_albedo = wl["no_albedo"]
+        params = list(sdf.parameters()) + list(var.parameters()) + ([] if no_albedo else list(col.parameters()))
+        red = FlatGradAllReducer(params)
+        opt = torch.optim.Adam(params, lr=5e-4)
+        host_b = [{k: v.pin_memory() for k, v in synth.make_batch(B, 3, True, 1 + rank, view=i).items()} for i in range(4)]
+        dev_b = [{k: v.to(dev) for k, v in hb.items()} for hb in host_b]
+        keys = ("rays_o", "rays_d", "near", "far", "lights_dir", "true_rgb", "mask")
+
+        def train(b):
+            red.zero()
+            out = renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
+                                             cos_anneal_ratio=1.0, no_albedo=no_albedo)
+            loss = loss_fn(out, b["true_rgb"], b["mask"])
+            loss.backward()
+            red.all_reduce()
+            return loss
+
+        step = lambda i: train(dev_b[i % 4])
+        for i in range(args.warmup):
+            step(i)
+        clk = ClockSampler(local)
+        L.profile_enable(True)
+        n0 = L.launch_count()
+        ms = timed(step, args.steps)
+        launches = L.launch_count() - n0
+        prof = L.profile_collect()
+        L.profile_enable(False)
+        clocks = clk.stop()
+
+        def e2e_step(i):
+            hb = host_b[i % 4]
+            b = {k: hb[k].to(dev, non_blocking=True) for k in keys}
+            loss = train(b)
+            return float(loss)                       # device -> host read of the step's result
+        ms_e2e = timed(e2e_step, args.steps)
+
+        def full_step(i):
+            step(i)
+            opt.step()
+        ms_full = timed(full_step, max(3, args.steps // 2))
+        units = B * world
+        h2d = sum(host_b[0][k].numel() * 4 for k in keys)
+        d2h = 4
+        unit = "rays/s"
+
+    value = units / ms * 1e3
+    e2e_val = units / ms_e2e * 1e3
+    # ---- roofline of the dominant tensor-core kernel, from the cudaEvent brackets recorded inside the timed region
+    kernels = {}
+    if args.workload == "grid512":
+        flops = {"sdf_fwd": FLOP_SDF_ONLY * units_launch}
+    else:
+        nf, nc = B * 128, B * 112
+        flops = {"sdf_fwd_grad": (FLOP_FWD_FULL + FLOP_DX) * nf, "sdf_bwd_data": FLOP_BWD_DATA * nf,
+                 "albedo_fwd": FLOP_ALB_FWD * nf, "albedo_bwd": 2 * 145664 * nf}
+        # dw_gemm launches: one for the SDF net, one for the albedo net per step
+        flops["dw_gemm"] = (FLOP_BWD_DW * nf + (0 if no_albedo else 2 * 145664 * nf)) / (1 if no_albedo else 2)
+    for name, (tot, cnt) in prof.items():
+        d = dict(ms_per_launch=tot / cnt, launches_per_step=cnt / args.steps, share_of_step=tot / (ms * args.steps))
+        if name in flops:
+            if name == "sdf_fwd" and args.workload != "grid512":
+                d["tflops"] = FLOP_SDF_ONLY * (B * 112) / (tot / args.steps) / 1e9
+            else:
+                d["tflops"] = flops[name] / (tot / cnt) / 1e9
+            d["frac_of_peak"] = d["tflops"] / pk["tf_sustained"]
+        kernels[name] = d
+    cand = [k for k in kernels if "tflops" in kernels[k]]
+    top = max(cand, key=lambda k: kernels[k]["share_of_step"]) if cand else None
+    roofline = None
+    if top:
+        roofline = dict(bound="tensor", kernel=top, achieved=kernels[top]["tflops"], peak=pk["tf_sustained"], unit="TFLOP/s",
+                        frac=kernels[top]["tflops"] / pk["tf_sustained"], traffic=None,
+                        peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})")
+    line = dict(metric=metric_name(args.workload), value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate",
+                data="synthetic", config=dict(workload=wl["desc"], weights="geometric init, torch.manual_seed(0)",
+                                              l2="per-step working set (activation streams, >1 GB) exceeds the 126 MB L2; "
+                                                 "4 input batches rotate", parallelism=f"dp{world}"),
+                clocks=clocks, e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                                        ms_per_step=ms_e2e),
+                gpu_launches=int(launches), roofline=roofline, kernels=kernels)
+    if args.workload != "grid512":
+        line["full_step_with_adam_ms"] = ms_full
+        line["algorithmic_tflops"] = FLOP_PER_RAY[not no_albedo] * units / ms / 1e9 / world
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, wl)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

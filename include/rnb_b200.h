@@ -164,6 +164,15 @@ RNB_API int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const 
                    const float* aux, void* scratch, float* d_normal, float* d_feat, float* dW0, float* db0, float* dW1,
                    float* db1, float* dW2, float* db2, void* stream);
 
+/* ---- instrumentation -------------------------------------------------------------------------------------- */
+/* total number of kernels this library has launched in this process */
+RNB_API long long rnb_launch_count(void);
+/* when enabled, every kernel launch is bracketed by cudaEvents on its stream; rnb_profile_collect synchronises the
+ * device and returns, per kernel name, the summed device time (ms) and the launch count since the last collect.
+ * names: max_tags rows of name_stride chars.  Returns the number of rows written. */
+RNB_API void rnb_profile_enable(int on);
+RNB_API int rnb_profile_collect(char* names, int name_stride, float* total_ms, int* counts, int max_tags);
+
 #ifdef __cplusplus
 }
 #endif

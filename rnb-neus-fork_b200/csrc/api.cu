@@ -5,6 +5,8 @@
 #include "render_params.h"
 #include "albedo_params.h"
 #include <algorithm>
+#include <vector>
+#include <cstring>
 
 namespace rnb {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -79,6 +81,37 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     return L;
 }
 
+
+// ---- optional per-kernel timing (cudaEvents on the launch stream) and a launch counter ------------------------
+enum ProfTag { T_SDF_PACK, T_SDF_FWD, T_SDF_FWD_GRAD, T_SDF_BWD_DATA, T_DW_GEMM, T_COLSUM, T_REDUCE, T_ABSMAX, T_SUM,
+               T_COARSE_Z, T_UPSAMPLE, T_FINAL_MERGE, T_COMPOSITE_FWD, T_COMPOSITE_BWD, T_ALBEDO_PACK, T_ALBEDO_FWD,
+               T_ALBEDO_BWD, T_SAMPLE_PDF, T_COUNT };
+static const char* const kProfNames[T_COUNT] = {
+    "sdf_pack", "sdf_fwd", "sdf_fwd_grad", "sdf_bwd_data", "dw_gemm", "colsum", "reduce", "absmax", "sum", "coarse_z",
+    "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf"};
+struct ProfRec { int tag; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static long long g_launches[T_COUNT] = {0};
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_ev_pool.empty()) { e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+template <class F>
+static cudaError_t profiled(int tag, cudaStream_t st, F&& f) {
+    ++g_launches[tag];
+    if (!g_prof_on) return f();
+    ProfRec r{tag, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    cudaError_t e = f();
+    cudaEventRecord(r.b, st);
+    g_prof.push_back(r);
+    return e;
+}
+
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -124,7 +157,7 @@ int64_t rnb_padded_points(int64_t n) { return (n + TILE_M - 1) / TILE_M * TILE_M
 size_t rnb_stream_bytes(int64_t n, int cols) { return (size_t)rnb_padded_points(n) * (size_t)cols * 2; }
 
 int rnb_sdf_pack(const float* const* W, const float* const* b, void* wblob, float* aux, void* stream) {
-    return (int)launch_sdf_pack(W, b, (uint8_t*)wblob, aux, (cudaStream_t)stream);
+    return (int)profiled(T_SDF_PACK, (cudaStream_t)stream, [&] { return launch_sdf_pack(W, b, (uint8_t*)wblob, aux, (cudaStream_t)stream); });
 }
 
 int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float* aux, float* out, float out_scale, void* stream) {
@@ -136,7 +169,7 @@ int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float* aux, fl
     table_forward(P.tab);
     P.out = out;
     P.out_scale = out_scale;
-    return (int)launch_sdf_fwd(P, sm_count(), (cudaStream_t)stream);
+    return (int)profiled(T_SDF_FWD, (cudaStream_t)stream, [&] { return launch_sdf_fwd(P, sm_count(), (cudaStream_t)stream); });
 }
 
 int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* aux, float* out_sdf, float* out_grad,
@@ -154,7 +187,7 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
     P.st_feat = (uint8_t*)st_feat; P.st_in0 = (uint8_t*)st_in0; P.st_in = (uint8_t*)st_in;
     P.st_s = (uint8_t*)st_s; P.st_w = (uint8_t*)st_w;
     P.stream_stride = rnb_stream_bytes(pts->n_pts, 256);
-    return (int)launch_sdf_fwd_grad(P, sm_count(), (cudaStream_t)stream);
+    return (int)profiled(T_SDF_FWD_GRAD, (cudaStream_t)stream, [&] { return launch_sdf_fwd_grad(P, sm_count(), (cudaStream_t)stream); });
 }
 
 
@@ -170,7 +203,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     uint8_t* sc = (uint8_t*)scratch;
     float* absmax = (float*)(sc + L.absmax);
     const size_t SS = rnb_stream_bytes(n, 256);
-    cudaError_t e = launch_absmax(d_sdf, n, d_grad, 3 * n, d_feat, d_feat ? 256 * n : 0, absmax, st);
+    cudaError_t e = profiled(T_ABSMAX, st, [&] { return launch_absmax(d_sdf, n, d_grad, 3 * n, d_feat, d_feat ? 256 * n : 0, absmax, st); });
     if (e != cudaSuccess) return (int)e;
     // ---- K3a: cotangent streams
     SdfBwdParams P{};
@@ -185,7 +218,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     P.st_s = (const uint8_t*)st_s; P.st_w = (const uint8_t*)st_w;
     P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_z2 = sc + L.z2; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;
     P.stream_stride = SS;
-    e = launch_sdf_bwd_data(P, sm_count(), st);
+    e = profiled(T_SDF_BWD_DATA, st, [&] { return launch_sdf_bwd_data(P, sm_count(), st); });
     if (e != cudaSuccess) return (int)e;
     // ---- K3b: dW_l = w_l^T uin_l + zbar_l^T in_l  (l = 0..7),  dW_8[1:] = dfeat^T in_8
     const int n_sub = (int)(rnb_padded_points(n) / 64);
@@ -222,7 +255,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
         r.use_cot_scale = 1; r.fold_xlo = l == 0; r.accumulate = 0;
         part += (size_t)L.dw_splits * 256 * j.nw;
     }
-    e = launch_dw_gemm(D, L.dw_splits, st);
+    e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
     if (e != cudaSuccess) return (int)e;
     // ---- bias gradients and the sdf row of W_8 (column sums over streams)
     ColsumParams C{};
@@ -252,39 +285,39 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
         r.dst = dW[8]; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = 1;
         r.partial2 = p1; r.splits2 = L.cs_splits; r.factor2 = 1.f; r.use_cot_scale2 = 0;
     }
-    e = launch_colsum(C, L.cs_splits, st);
+    e = profiled(T_COLSUM, st, [&] { return launch_colsum(C, L.cs_splits, st); });
     if (e != cudaSuccess) return (int)e;
-    e = launch_reduce(R, st);
+    e = profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
     if (e != cudaSuccess) return (int)e;
-    return (int)launch_sum(d_sdf, n, db[8], st);
+    return (int)profiled(T_SUM, st, [&] { return launch_sum(d_sdf, n, db[8], st); });
 }
 
 
 int rnb_coarse_z(const float* near, const float* far, const float* t_rand, float* z, int n_rays, int n_samples, void* stream) {
-    return (int)launch_coarse_z(near, far, t_rand, z, n_rays, n_samples, (cudaStream_t)stream);
+    return (int)profiled(T_COARSE_Z, (cudaStream_t)stream, [&] { return launch_coarse_z(near, far, t_rand, z, n_rays, n_samples, (cudaStream_t)stream); });
 }
 int rnb_upsample_step(const rnb_upsample_t* p, void* stream) {
     if (p->n_old + p->n_merge > MAX_RAY_SAMPLES || p->n_new > 32) return (int)cudaErrorInvalidValue;
-    return (int)launch_upsample(*p, (cudaStream_t)stream);
+    return (int)profiled(T_UPSAMPLE, (cudaStream_t)stream, [&] { return launch_upsample(*p, (cudaStream_t)stream); });
 }
 int rnb_sample_pdf_from_cdf(const float* bins, const float* cdf, int n_rays, int n, int n_new, float* samples, int64_t* inds,
                             void* stream) {
-    return (int)launch_sample_pdf_from_cdf(bins, cdf, n_rays, n, n_new, samples, inds, (cudaStream_t)stream);
+    return (int)profiled(T_SAMPLE_PDF, (cudaStream_t)stream, [&] { return launch_sample_pdf_from_cdf(bins, cdf, n_rays, n, n_new, samples, inds, (cudaStream_t)stream); });
 }
 int rnb_final_merge(const float* z_old, int n_old, const float* z_new, int n_new, int n_rays, float sample_dist, float* z_out,
                     float* mid_out, void* stream) {
     if (n_old + n_new > MAX_RAY_SAMPLES) return (int)cudaErrorInvalidValue;
-    return (int)launch_final_merge(z_old, n_old, z_new, n_new, n_rays, sample_dist, z_out, mid_out, (cudaStream_t)stream);
+    return (int)profiled(T_FINAL_MERGE, (cudaStream_t)stream, [&] { return launch_final_merge(z_old, n_old, z_new, n_new, n_rays, sample_dist, z_out, mid_out, (cudaStream_t)stream); });
 }
-int rnb_composite_fwd(const rnb_composite_t* p, void* stream) { return (int)launch_composite(*p, false, (cudaStream_t)stream); }
-int rnb_composite_bwd(const rnb_composite_t* p, void* stream) { return (int)launch_composite(*p, true, (cudaStream_t)stream); }
+int rnb_composite_fwd(const rnb_composite_t* p, void* stream) { return (int)profiled(T_COMPOSITE_FWD, (cudaStream_t)stream, [&] { return launch_composite(*p, false, (cudaStream_t)stream); }); }
+int rnb_composite_bwd(const rnb_composite_t* p, void* stream) { return (int)profiled(T_COMPOSITE_BWD, (cudaStream_t)stream, [&] { return launch_composite(*p, true, (cudaStream_t)stream); }); }
 
 
 size_t rnb_albedo_wblob_bytes(void) { return ALBW_BYTES; }
 size_t rnb_albedo_aux_floats(void) { return ALBX_FLOATS; }
 int rnb_albedo_pack(const float* W0, const float* b0, const float* W1, const float* b1, const float* W2, const float* b2,
                     void* wblob, float* aux, void* stream) {
-    return (int)launch_albedo_pack(W0, b0, W1, b1, W2, b2, (uint8_t*)wblob, aux, (cudaStream_t)stream);
+    return (int)profiled(T_ALBEDO_PACK, (cudaStream_t)stream, [&] { return launch_albedo_pack(W0, b0, W1, b1, W2, b2, (uint8_t*)wblob, aux, (cudaStream_t)stream); });
 }
 
 int rnb_albedo_fwd(const rnb_points_t* pts, const float* normals, const void* st_feat, const void* wblob, const float* aux,
@@ -299,7 +332,7 @@ int rnb_albedo_fwd(const rnb_points_t* pts, const float* normals, const void* st
     add_step(P.tab, ALBW_F1, 256, 256);
     P.normals = normals; P.st_feat = (const uint8_t*)st_feat; P.albedo = albedo;
     P.st_pe = (uint8_t*)st_pe; P.st_h0 = (uint8_t*)st_h0; P.st_h1 = (uint8_t*)st_h1;
-    return (int)launch_albedo_fwd(P, sm_count(), (cudaStream_t)stream);
+    return (int)profiled(T_ALBEDO_FWD, (cudaStream_t)stream, [&] { return launch_albedo_fwd(P, sm_count(), (cudaStream_t)stream); });
 }
 
 size_t rnb_albedo_bwd_scratch_bytes(int64_t n_pts) { return albedo_bwd_scratch(n_pts).total; }
@@ -315,7 +348,7 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     uint8_t* sc = (uint8_t*)scratch;
     float* absmax = (float*)(sc + L.absmax);
     const int64_t n_pad = rnb_padded_points(n);
-    cudaError_t e = launch_absmax(d_albedo, 3 * n, nullptr, 0, nullptr, 0, absmax, st);
+    cudaError_t e = profiled(T_ABSMAX, st, [&] { return launch_absmax(d_albedo, 3 * n, nullptr, 0, nullptr, 0, absmax, st); });
     if (e != cudaSuccess) return (int)e;
     AlbedoBwdParams P{};
     P.src = to_src(pts);
@@ -331,7 +364,7 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     P.dz2 = (float*)(sc + L.dz2);
     P.st_dz1 = sc + L.dz1; P.st_dz0 = sc + L.dz0;
     P.d_feat = d_feat; P.d_normal = d_normal;
-    e = launch_albedo_bwd(P, sm_count(), st);
+    e = profiled(T_ALBEDO_BWD, st, [&] { return launch_albedo_bwd(P, sm_count(), st); });
     if (e != cudaSuccess) return (int)e;
     const int n_sub = (int)(n_pad / 64);
     DwParams D{};
@@ -351,7 +384,7 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256);
     add_dw(sc + L.dz0, (const uint8_t*)st_feat, 32, 256, dW0, 310, 54, 256);
     add_dw(sc + L.dz0, (const uint8_t*)st_pe, 8, 64, dW0, 310, 0, 54);
-    e = launch_dw_gemm(D, L.dw_splits, st);
+    e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
     if (e != cudaSuccess) return (int)e;
     ColsumParams C{};
     C.n_sub = n_sub;
@@ -368,15 +401,45 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     add_cs(sc + L.dz1, nullptr, db1, 1);
     add_cs(sc + L.dz0, nullptr, db0, 1);
     for (int k = 0; k < 3; ++k) add_cs((const uint8_t*)st_h1, P.dz2 + (size_t)k * n_pad, dW2 + k * 256, 0);
-    e = launch_colsum(C, L.cs_splits, st);
+    e = profiled(T_COLSUM, st, [&] { return launch_colsum(C, L.cs_splits, st); });
     if (e != cudaSuccess) return (int)e;
-    e = launch_reduce(R, st);
+    e = profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
     if (e != cudaSuccess) return (int)e;
     for (int k = 0; k < 3; ++k) {
-        e = launch_sum(P.dz2 + (size_t)k * n_pad, n_pad, db2 + k, st);
+        e = profiled(T_SUM, st, [&] { return launch_sum(P.dz2 + (size_t)k * n_pad, n_pad, db2 + k, st); });
         if (e != cudaSuccess) return (int)e;
     }
     return 0;
+}
+
+
+void rnb_profile_enable(int on) { g_prof_on = on != 0; }
+long long rnb_launch_count(void) {
+    long long n = 0;
+    for (int t = 0; t < T_COUNT; ++t) n += g_launches[t];
+    return n;
+}
+int rnb_profile_collect(char* names, int name_stride, float* total_ms, int* counts, int max_tags) {
+    cudaDeviceSynchronize();
+    float ms[T_COUNT] = {0};
+    int cnt[T_COUNT] = {0};
+    for (const ProfRec& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.tag] += t; ++cnt[r.tag]; }
+        g_ev_pool.push_back(r.a);
+        g_ev_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    int n = 0;
+    for (int t = 0; t < T_COUNT && n < max_tags; ++t) {
+        if (!cnt[t]) continue;
+        std::strncpy(names + (size_t)n * name_stride, kProfNames[t], name_stride - 1);
+        names[(size_t)n * name_stride + name_stride - 1] = 0;
+        total_ms[n] = ms[t];
+        counts[n] = cnt[t];
+        ++n;
+    }
+    return n;
 }
 
 }  // extern "C"

@@ -62,6 +62,9 @@ _SIGNATURES = {
     "rnb_albedo_fwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 9),
     "rnb_albedo_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "rnb_albedo_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 19),
+    "rnb_launch_count": (C.c_longlong, []),
+    "rnb_profile_enable": (None, [C.c_int]),
+    "rnb_profile_collect": (C.c_int, [C.c_char_p, C.c_int, _VP, _VP, C.c_int]),
     "rnb_coarse_z": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
     "rnb_upsample_step": (C.c_int, [C.POINTER(Upsample), _VP]),
     "rnb_sample_pdf_from_cdf": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP]),
@@ -89,6 +92,28 @@ def load():
 
 def exported_symbols():
     return sorted(_SIGNATURES)
+
+
+def profile_enable(on: bool):
+    load().rnb_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """-> {kernel name: (total device ms, launches)} since the last collect (synchronises the device)."""
+    lib = load()
+    max_tags, stride = 32, 32
+    names = C.create_string_buffer(max_tags * stride)
+    ms = (C.c_float * max_tags)()
+    cnt = (C.c_int * max_tags)()
+    n = lib.rnb_profile_collect(names, stride, C.cast(ms, C.c_void_p), C.cast(cnt, C.c_void_p), max_tags)
+    out = {}
+    for i in range(n):
+        out[names.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()] = (float(ms[i]), int(cnt[i]))
+    return out
+
+
+def launch_count() -> int:
+    return int(load().rnb_launch_count())
 
 
 def check(code: int, what: str):
