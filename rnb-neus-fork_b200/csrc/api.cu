@@ -131,8 +131,11 @@ static SdfPointSource to_src(const rnb_points_t* p) {
     return s;
 }
 
-static void add_step(ChainTable& t, uint32_t off, int n, int k, int accumulate = 0) {
+static void add_step(ChainTable& t, uint32_t off, int n, int k, int accumulate = 0, const void* pf0 = nullptr,
+                     const void* pf1 = nullptr) {
     t.steps[t.n_steps].accumulate = (uint32_t)accumulate;
+    t.steps[t.n_steps].pf[0] = (const uint8_t*)pf0;
+    t.steps[t.n_steps].pf[1] = (const uint8_t*)pf1;
     t.steps[t.n_steps].w_off = off;
     t.steps[t.n_steps].n = (uint16_t)n;
     t.steps[t.n_steps].k = (uint16_t)k;
@@ -181,7 +184,10 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
     P.aux = aux;
     table_forward(P.tab);
     add_step(P.tab, SDFW_F8, 256, 256);
-    for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256);
+    {
+        const size_t SS = rnb_stream_bytes(pts->n_pts, 256);
+        for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256, 0, (const uint8_t*)st_s + (size_t)(l - 1) * SS);
+    }
     add_step(P.tab, sdfw_tr(0), 64, 256);
     P.out_sdf = out_sdf; P.out_grad = out_grad; P.out_full = out_full;
     P.st_feat = (uint8_t*)st_feat; P.st_in0 = (uint8_t*)st_in0; P.st_in = (uint8_t*)st_in;
@@ -211,9 +217,12 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     P.n_tiles = n_tiles(n);
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
-    table_forward(P.tab);
-    add_step(P.tab, SDFW_T8, 256, 256);
-    for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256);
+    add_step(P.tab, sdfw_fwd(0), 256, 64, 0, st_s, st_w);
+    for (int l = 1; l < 8; ++l)
+        add_step(P.tab, sdfw_fwd(l), 256, 256, 0, (const uint8_t*)st_s + (size_t)l * SS, (const uint8_t*)st_w + (size_t)l * SS);
+    add_step(P.tab, SDFW_T8, 256, 256, 0, (const uint8_t*)st_s + (size_t)7 * SS, sc + L.z2 + (size_t)7 * SS);
+    for (int l = 7; l >= 1; --l)
+        add_step(P.tab, sdfw_tr(l), 256, 256, 0, (const uint8_t*)st_s + (size_t)(l - 1) * SS, sc + L.z2 + (size_t)(l - 1) * SS);
     P.d_sdf = d_sdf; P.d_grad = d_grad; P.d_feat = d_feat; P.cot_absmax = absmax;
     P.st_s = (const uint8_t*)st_s; P.st_w = (const uint8_t*)st_w;
     P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_z2 = sc + L.z2; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;

@@ -26,6 +26,9 @@ struct ChainStep {
     uint16_t n;       // UMMA N (rows of the weight image), multiple of 16, <= 256
     uint16_t k;       // K, multiple of 32
     uint32_t accumulate;   // 1: add onto the accumulator left by the previous step (split-K over two A operands)
+    // 256-wide fp16 streams this step's EPILOGUE reads (0 = none): the producer warp pulls the tile's 64 KB of each
+    // into L2 one step ahead with cp.async.bulk.prefetch, so the per-row loads of the epilogue are L2 hits
+    const uint8_t* pf[2];
 };
 struct ChainTable {
     int n_steps;
@@ -85,10 +88,26 @@ __device__ __forceinline__ void chain_teardown(const ChainSmem& s, uint32_t tmem
 }
 
 // warp 0, one lane
+__device__ __forceinline__ void chain_prefetch_step(const ChainTable& tab, int st, int64_t tile) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint8_t* b = tab.steps[st].pf[k];
+        if (b) {
+            bulk_prefetch_l2(b + (size_t)tile * 65536, 32768);
+            bulk_prefetch_l2(b + (size_t)tile * 65536 + 32768, 32768);
+        }
+    }
+}
+
 __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTable& tab, const uint8_t* wblob, int n_my_tiles) {
     uint32_t it = 0;
     for (int t = 0; t < n_my_tiles; ++t) {
+        const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+        if (t == 0) chain_prefetch_step(tab, 0, tile);
         for (int st = 0; st < tab.n_steps; ++st) {
+            // one step of lead: the streams of step st+1 (or of the next tile's step 0)
+            if (st + 1 < tab.n_steps) chain_prefetch_step(tab, st + 1, tile);
+            else if (t + 1 < n_my_tiles) chain_prefetch_step(tab, 0, tile + gridDim.x);
             const uint32_t bytes = 64u * tab.steps[st].n;                 // 4 chunks x n rows x 16 B
             const uint8_t* src = wblob + tab.steps[st].w_off;
             const int nsl = tab.steps[st].k >> 5;

@@ -260,17 +260,27 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             float g[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int l = 7; l >= 1; --l) {
-                ep.wait_acc();
                 const uint8_t* st_sp = P.st_s + (size_t)(l - 1) * SS;
                 uint8_t* st_wp = P.st_w + (size_t)(l - 1) * SS;
+                uint4 hs_n[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hs_n[q] = ld_stream(st_sp, p, q, 32);
+                ep.wait_acc();
 #pragma unroll 1
                 for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint4 hs_c[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) hs_c[q] = hs_n[q];
+                    if (c0 + 32 < 256) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) hs_n[q] = ld_stream(st_sp, p, (c0 >> 3) + 4 + q, 32);
+                    }
                     uint32_t v[32];
                     ep.ld_acc(c0, v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int ch = (c0 >> 3) + q;
-                        const uint4 hs = ld_stream(st_sp, p, ch, 32);
+                        const uint4 hs = hs_c[q];
                         const float2 s0 = unpack_h2(hs.x), s1 = unpack_h2(hs.y), s2 = unpack_h2(hs.z), s3 = unpack_h2(hs.w);
                         float u[8];
 #pragma unroll
@@ -363,20 +373,33 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
             // ---------------- phase A, l = 0..7:  wbar = W_l uin_l ;  z2_l = 100(1-s)w*wbar ;  ua_bar = s*wbar
 #pragma unroll 1
             for (int l = 0; l < 8; ++l) {
-                ep.wait_acc();
                 const uint8_t* st_s = P.st_s + (size_t)l * SS;
                 const uint8_t* st_w = P.st_w + (size_t)l * SS;
                 uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
                 uint8_t* st_un = P.st_uin + (size_t)l * SS;          // uin_{l+1} = ua_bar_l
+                uint4 hs_n[4], hw_n[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hs_n[q] = ld_stream(st_s, p, q, 32); hw_n[q] = ld_stream(st_w, p, q, 32); }
+                ep.wait_acc();
 #pragma unroll 1
                 for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint4 hs_c[4], hw_c[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { hs_c[q] = hs_n[q]; hw_c[q] = hw_n[q]; }
+                    if (c0 + 32 < 256) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 4 + q, 32);
+                            hw_n[q] = ld_stream(st_w, p, (c0 >> 3) + 4 + q, 32);
+                        }
+                    }
                     uint32_t v[32];
                     ep.ld_acc(c0, v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int ch = (c0 >> 3) + q;
-                        const uint4 hs = ld_stream(st_s, p, ch, 32);
-                        const uint4 hw = ld_stream(st_w, p, ch, 32);
+                        const uint4 hs = hs_c[q];
+                        const uint4 hw = hw_c[q];
                         const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hwa[4] = {hw.x, hw.y, hw.z, hw.w};
                         uint32_t z2[4], ub[4];
 #pragma unroll
@@ -422,19 +445,32 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
             // ---------------- phase B: GEMM yields abar_l (l = 7..0);  zbar_l = s_l*abar_l + z2_l
 #pragma unroll 1
             for (int l = 7; l >= 0; --l) {
-                ep.wait_acc();
                 const uint8_t* st_s = P.st_s + (size_t)l * SS;
                 const uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
                 uint8_t* st_zb = P.st_zbar + (size_t)l * SS;
+                uint4 hs_n[4], hz_n[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hs_n[q] = ld_stream(st_s, p, q, 32); hz_n[q] = ld_stream(st_z2, p, q, 32); }
+                ep.wait_acc();
 #pragma unroll 1
                 for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint4 hs_c[4], hz_c[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { hs_c[q] = hs_n[q]; hz_c[q] = hz_n[q]; }
+                    if (c0 + 32 < 256) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 4 + q, 32);
+                            hz_n[q] = ld_stream(st_z2, p, (c0 >> 3) + 4 + q, 32);
+                        }
+                    }
                     uint32_t v[32];
                     ep.ld_acc(c0, v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int ch = (c0 >> 3) + q;
-                        const uint4 hs = ld_stream(st_s, p, ch, 32);
-                        const uint4 hz = ld_stream(st_z2, p, ch, 32);
+                        const uint4 hs = hs_c[q];
+                        const uint4 hz = hz_c[q];
                         const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
                         float ww[8];
                         if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
