@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
             const bool live = p < P.src.n_pts;
             // A <- feature tile (already fp16, chunked)
-#pragma unroll 4
+#pragma unroll 8
             for (int ch = 0; ch < 32; ++ch) ep.st_a(ch, ld_stream(P.st_feat, p, ch, 32));
             ep.signal();
             // step 0a done (features consumed): A[:, 0:64] <- positional encodings
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
 #pragma unroll
             for (int k = 0; k < 3; ++k) P.dz2[(size_t)k * P.n_pad + p] = dz2[k];
             // dz1 = (W2^T dz2) * (h1 > 0)
-#pragma unroll 1
+#pragma unroll 4
             for (int ch = 0; ch < 32; ++ch) {
                 const uint4 hh = ld_stream(P.st_h1, p, ch, 32);
                 const uint32_t ha[4] = {hh.x, hh.y, hh.z, hh.w};
@@ -173,27 +173,39 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
             }
             ep.signal();
             // step B1: dh0 = dz1 W1 ; dz0 = dh0 * (h0 > 0)
-            ep.wait_acc();
+            {
+                uint4 hh_n[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hh_n[q] = ld_stream(P.st_h0, p, q, 32);
+                ep.wait_acc();
 #pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t v[32];
-                ep.ld_acc(c0, v);
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint4 hh_c[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int ch = (c0 >> 3) + q;
-                    const uint4 hh = ld_stream(P.st_h0, p, ch, 32);
-                    const uint32_t ha[4] = {hh.x, hh.y, hh.z, hh.w};
-                    uint32_t o[4];
+                    for (int q = 0; q < 4; ++q) hh_c[q] = hh_n[q];
+                    if (c0 + 32 < 256) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 hv = unpack_h2(ha[j]);
-                        const float d0 = hv.x > 0.f ? __uint_as_float(v[q * 8 + 2 * j]) : 0.f;
-                        const float d1 = hv.y > 0.f ? __uint_as_float(v[q * 8 + 2 * j + 1]) : 0.f;
-                        o[j] = pack_h2_sat(d0, d1);
+                        for (int q = 0; q < 4; ++q) hh_n[q] = ld_stream(P.st_h0, p, (c0 >> 3) + 4 + q, 32);
                     }
-                    const uint4 u = make_uint4(o[0], o[1], o[2], o[3]);
-                    ep.st_a(ch, u);
-                    st_stream(P.st_dz0, p, ch, 32, u);
+                    uint32_t v[32];
+                    ep.ld_acc(c0, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ch = (c0 >> 3) + q;
+                        const uint4 hh = hh_c[q];
+                        const uint32_t ha[4] = {hh.x, hh.y, hh.z, hh.w};
+                        uint32_t o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 hv = unpack_h2(ha[j]);
+                            const float d0 = hv.x > 0.f ? __uint_as_float(v[q * 8 + 2 * j]) : 0.f;
+                            const float d1 = hv.y > 0.f ? __uint_as_float(v[q * 8 + 2 * j + 1]) : 0.f;
+                            o[j] = pack_h2_sat(d0, d1);
+                        }
+                        const uint4 u = make_uint4(o[0], o[1], o[2], o[3]);
+                        ep.st_a(ch, u);
+                        st_stream(P.st_dz0, p, ch, 32, u);
+                    }
                 }
             }
             ep.signal();

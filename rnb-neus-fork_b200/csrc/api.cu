@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace rnb {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -34,7 +35,7 @@ cudaError_t launch_albedo_fwd(const AlbedoFwdParams& P, int sm_count, cudaStream
 cudaError_t launch_albedo_bwd(const AlbedoBwdParams& P, int sm_count, cudaStream_t st);
 
 struct AlbedoBwdScratch {
-    size_t absmax, dz2, dz1, dz0, dw_part, cs_part, total;
+    size_t absmax, dz2, dz1, dz0, dw_part, dwcs_part, cs_part, total;
     int dw_splits, cs_splits;
 };
 static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
@@ -51,6 +52,7 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
     L.dz0 = o; o += s256;
     o = align_up(o, 256);
     L.dw_part = o; o += (size_t)L.dw_splits * 256 * (256 + 256 + 64) * 4;
+    L.dwcs_part = o; o += (size_t)L.dw_splits * 256 * 2 * 4;
     L.cs_part = o; o += (size_t)L.cs_splits * 256 * 5 * 4;
     L.total = align_up(o, 256);
     return L;
@@ -58,7 +60,7 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
 
 // scratch layout of rnb_sdf_bwd
 struct SdfBwdScratch {
-    size_t absmax, uin0, uin, z2, zbar, dfeat, dw_part, cs_part, total;
+    size_t absmax, uin0, uin, z2, zbar, dfeat, dw_part, dwcs_part, cs_part, total;
     int dw_splits, cs_splits;
 };
 static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
@@ -76,6 +78,7 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     L.dfeat = o; o += s256;
     o = align_up(o, 256);
     L.dw_part = o; o += (size_t)L.dw_splits * 256 * (64 + 8 * 256) * 4;
+    L.dwcs_part = o; o += (size_t)L.dw_splits * 256 * 9 * 4;
     L.cs_part = o; o += (size_t)L.cs_splits * 256 * 12 * 4;
     L.total = align_up(o, 256);
     return L;
@@ -134,8 +137,9 @@ static SdfPointSource to_src(const rnb_points_t* p) {
 static void add_step(ChainTable& t, uint32_t off, int n, int k, int accumulate = 0, const void* pf0 = nullptr,
                      const void* pf1 = nullptr) {
     t.steps[t.n_steps].accumulate = (uint32_t)accumulate;
-    t.steps[t.n_steps].pf[0] = (const uint8_t*)pf0;
-    t.steps[t.n_steps].pf[1] = (const uint8_t*)pf1;
+    static const int pf_mode = getenv("RNB_PF") ? atoi(getenv("RNB_PF")) : 3;   // bit0: first stream, bit1: second
+    t.steps[t.n_steps].pf[0] = (pf_mode & 1) ? (const uint8_t*)pf0 : nullptr;
+    t.steps[t.n_steps].pf[1] = (pf_mode & 2) ? (const uint8_t*)pf1 : nullptr;
     t.steps[t.n_steps].w_off = off;
     t.steps[t.n_steps].n = (uint16_t)n;
     t.steps[t.n_steps].k = (uint16_t)k;
@@ -217,12 +221,11 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     P.n_tiles = n_tiles(n);
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
-    add_step(P.tab, sdfw_fwd(0), 256, 64, 0, st_s, st_w);
-    for (int l = 1; l < 8; ++l)
-        add_step(P.tab, sdfw_fwd(l), 256, 256, 0, (const uint8_t*)st_s + (size_t)l * SS, (const uint8_t*)st_w + (size_t)l * SS);
-    add_step(P.tab, SDFW_T8, 256, 256, 0, (const uint8_t*)st_s + (size_t)7 * SS, sc + L.z2 + (size_t)7 * SS);
-    for (int l = 7; l >= 1; --l)
-        add_step(P.tab, sdfw_tr(l), 256, 256, 0, (const uint8_t*)st_s + (size_t)(l - 1) * SS, sc + L.z2 + (size_t)(l - 1) * SS);
+    // no L2 prefetch here: measured, this kernel runs at ~65 % of HBM bandwidth and a producer-side prefetch of its
+    // streams raised DRAM reads by 75 % (6.5 ms without, 7.6 ms with, 1 M points)
+    table_forward(P.tab);
+    add_step(P.tab, SDFW_T8, 256, 256);
+    for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256);
     P.d_sdf = d_sdf; P.d_grad = d_grad; P.d_feat = d_feat; P.cot_absmax = absmax;
     P.st_s = (const uint8_t*)st_s; P.st_w = (const uint8_t*)st_w;
     P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_z2 = sc + L.z2; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;
@@ -236,6 +239,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     ReduceParams R{};
     R.cot_absmax = absmax;
     float* part = (float*)(sc + L.dw_part);
+    float* dwcs = (float*)(sc + L.dwcs_part);
     const uint8_t* in0 = (const uint8_t*)st_in0;
     const uint8_t* inl = (const uint8_t*)st_in;
     const uint8_t* sw = (const uint8_t*)st_w;
@@ -256,6 +260,16 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
         }
         j.b_chunks[0] = j.b_chunks[1] = j.nw / 8;
         j.partial = part;
+        // bias gradient db_l = column sums of zbar_l (dfeat for l = 8), taken from the staged A tile inside the GEMM
+        j.colsum_pair = l < 8 ? 1 : 0;
+        j.cs_partial = dwcs;
+        {
+            ReduceJob& rb = R.jobs[R.n_jobs++];
+            rb.partial = dwcs; rb.splits = L.dw_splits; rb.rows = 1; rb.nw = 256;
+            rb.dst = db[l]; rb.dst_pitch = 0; rb.dst_row0 = 0; rb.dst_col0 = l == 8 ? 1 : 0;
+            rb.out_rows = 1; rb.out_cols = l == 3 ? 217 : 256; rb.factor = 1.f; rb.use_cot_scale = 1;
+            dwcs += (size_t)L.dw_splits * 256;
+        }
         ReduceJob& r = R.jobs[R.n_jobs++];
         r.partial = part; r.splits = L.dw_splits; r.rows = 256; r.nw = j.nw;
         r.dst = dW[l]; r.dst_pitch = l == 0 ? 39 : 256; r.dst_row0 = l == 8 ? 1 : 0; r.dst_col0 = 0;
@@ -278,13 +292,6 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
         cpart += (size_t)L.cs_splits * 256;
         return p0;
     };
-    for (int l = 0; l < 9; ++l) {
-        const float* p0 = add_cs(l < 8 ? sc + L.zbar + (size_t)l * SS : sc + L.dfeat, nullptr);
-        ReduceJob& r = R.jobs[R.n_jobs++];
-        r.partial = p0; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
-        r.dst = db[l]; r.dst_pitch = 0; r.dst_row0 = 0; r.dst_col0 = l == 8 ? 1 : 0;
-        r.out_rows = 1; r.out_cols = l == 3 ? 217 : 256; r.factor = 1.f; r.use_cot_scale = 1;
-    }
     {
         // dW_8[0,:] = sum_p uabar_7[p,:]  +  sum_p d_sdf[p] a_7[p,:]
         const float* p0 = add_cs(sc + L.uin + (size_t)7 * SS, nullptr);
@@ -381,18 +388,29 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     ReduceParams R{};
     R.cot_absmax = absmax;
     float* part = (float*)(sc + L.dw_part);
-    auto add_dw = [&](const uint8_t* a, const uint8_t* b, int b_chunks, int nw, float* dst, int pitch, int col0, int out_cols) {
+    float* dwcs = (float*)(sc + L.dwcs_part);
+    auto add_dw = [&](const uint8_t* a, const uint8_t* b, int b_chunks, int nw, float* dst, int pitch, int col0, int out_cols,
+                      float* db_dst) {
         DwJob& j = D.jobs[D.n_jobs++];
         j.n_pairs = 1; j.a[0] = a; j.b[0] = b; j.b_chunks[0] = b_chunks; j.b_chunk0 = 0; j.nw = nw; j.partial = part;
+        j.colsum_pair = -1;
+        if (db_dst) {
+            j.colsum_pair = 0;
+            j.cs_partial = dwcs;
+            ReduceJob& rb = R.jobs[R.n_jobs++];
+            rb.partial = dwcs; rb.splits = L.dw_splits; rb.rows = 1; rb.nw = 256;
+            rb.dst = db_dst; rb.dst_pitch = 0; rb.out_rows = 1; rb.out_cols = 256; rb.factor = 1.f; rb.use_cot_scale = 1;
+            dwcs += (size_t)L.dw_splits * 256;
+        }
         ReduceJob& r = R.jobs[R.n_jobs++];
         r.partial = part; r.splits = L.dw_splits; r.rows = 256; r.nw = nw;
         r.dst = dst; r.dst_pitch = pitch; r.dst_row0 = 0; r.dst_col0 = col0; r.out_rows = 256; r.out_cols = out_cols;
         r.factor = 1.f; r.use_cot_scale = 1;
         part += (size_t)L.dw_splits * 256 * nw;
     };
-    add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256);
-    add_dw(sc + L.dz0, (const uint8_t*)st_feat, 32, 256, dW0, 310, 54, 256);
-    add_dw(sc + L.dz0, (const uint8_t*)st_pe, 8, 64, dW0, 310, 0, 54);
+    add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256, db1);
+    add_dw(sc + L.dz0, (const uint8_t*)st_feat, 32, 256, dW0, 310, 54, 256, db0);
+    add_dw(sc + L.dz0, (const uint8_t*)st_pe, 8, 64, dW0, 310, 0, 54, nullptr);
     e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
     if (e != cudaSuccess) return (int)e;
     ColsumParams C{};
@@ -407,8 +425,6 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
         r.dst = dst; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = use_scale;
         cpart += (size_t)L.cs_splits * 256;
     };
-    add_cs(sc + L.dz1, nullptr, db1, 1);
-    add_cs(sc + L.dz0, nullptr, db0, 1);
     for (int k = 0; k < 3; ++k) add_cs((const uint8_t*)st_h1, P.dz2 + (size_t)k * n_pad, dW2 + k * 256, 0);
     e = profiled(T_COLSUM, st, [&] { return launch_colsum(C, L.cs_splits, st); });
     if (e != cudaSuccess) return (int)e;

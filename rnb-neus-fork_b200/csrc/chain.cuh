@@ -103,11 +103,11 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
     uint32_t it = 0;
     for (int t = 0; t < n_my_tiles; ++t) {
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
-        if (t == 0) chain_prefetch_step(tab, 0, tile);
         for (int st = 0; st < tab.n_steps; ++st) {
-            // one step of lead: the streams of step st+1 (or of the next tile's step 0)
-            if (st + 1 < tab.n_steps) chain_prefetch_step(tab, st + 1, tile);
-            else if (t + 1 < n_my_tiles) chain_prefetch_step(tab, 0, tile + gridDim.x);
+            // The producer reaches step st's first weight slice while MMA(st-1) is still running, i.e. about one
+            // epilogue + one MMA phase before epilogue(st) reads these streams: enough to cover DRAM latency, short
+            // enough that the lines are still in L2 (a longer lead measurably doubled DRAM reads).
+            chain_prefetch_step(tab, st, tile);
             const uint32_t bytes = 64u * tab.steps[st].n;                 // 4 chunks x n rows x 16 B
             const uint8_t* src = wblob + tab.steps[st].w_off;
             const int nsl = tab.steps[st].k >> 5;
@@ -196,8 +196,10 @@ struct Epi {
 __device__ __forceinline__ size_t stream_off(int64_t p, int chunk, int nchunks) {
     return ((size_t)((p >> 6) * nchunks + chunk) * 64 + (size_t)(p & 63)) * 16;
 }
+// streams are written once and read by a later kernel (or many steps later): evict-first (.cs) keeps them from
+// pushing the prefetched operands of the next step out of L2
 __device__ __forceinline__ void st_stream(uint8_t* base, int64_t p, int chunk, int nchunks, uint4 v) {
-    *reinterpret_cast<uint4*>(base + stream_off(p, chunk, nchunks)) = v;
+    __stcs(reinterpret_cast<uint4*>(base + stream_off(p, chunk, nchunks)), v);
 }
 __device__ __forceinline__ uint4 ld_stream(const uint8_t* base, int64_t p, int chunk, int nchunks) {
     return *reinterpret_cast<const uint4*>(base + stream_off(p, chunk, nchunks));

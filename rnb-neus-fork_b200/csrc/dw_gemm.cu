@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const __grid_con
     const uint32_t b_bytes = (uint32_t)(nw >> 3) * 1024u;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        // empty[]: the MMA commit + one arrival per epilogue warp (they read the A tile for the column sums)
+        for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 4); }
         mbar_init(acc_full, 1);
         mbar_fence_init();
     }
@@ -82,9 +83,40 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const __grid_con
             umma_commit(acc_full);
         }
     } else {
-        // epilogue: dump the two 128-row halves of the accumulator as one fp32 partial [256][nw]
+        // While the MMAs run these four warps are idle: they column-sum the flagged A-side tile straight from the
+        // staged shared memory (db_l = sum_p zbar_l[p,:]), then dump the accumulator.
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;            // 0..127
+        const int cs_row = et & 63, cs_cg = et >> 6;      // thread owns point row cs_row and chunks cs_cg*16 .. +15
+        float cs[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) cs[i] = 0.f;
+        {
+            uint32_t it = 0;
+            for (int sub = sub0; sub < sub1; ++sub)
+                for (int pr = 0; pr < job.n_pairs; ++pr, ++it) {
+                    const uint32_t slot = it % DW_STAGES, ph = (it / DW_STAGES) & 1;
+                    // always observe the fill of this use before arriving on empty[]: keeps every arrival in its own phase
+                    mbar_wait(&full[slot], ph);
+                    if (pr == job.colsum_pair) {
+                        const uint8_t* a_tile = smem + slot * DW_STAGE;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(a_tile + ((size_t)(cs_cg * 16 + c) * 64 + cs_row) * 16);
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = unpack_h2(w[j]);
+                                cs[c * 8 + 2 * j] += f.x;
+                                cs[c * 8 + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[slot]);
+                }
+        }
         float* out = job.partial + (size_t)split * 256 * nw;
         if (sub1 > sub0) {
             mbar_wait(acc_full, 0);
@@ -105,6 +137,28 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const __grid_con
         } else {
             for (int h = 0; h < 2; ++h)
                 for (int c = 0; c < nw; ++c) out[(size_t)(h * 128 + row) * nw + c] = 0.f;
+        }
+        if (job.colsum_pair >= 0) {
+            // reduce over the 64 point rows: lanes of a warp hold 32 rows, warps (2,3) / (4,5) hold the two halves
+#pragma unroll
+            for (int i = 0; i < 128; ++i) {
+                float v = cs[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                cs[i] = v;
+            }
+            // the ring is drained (acc_full passed): reuse its first bytes as scratch for the cross-warp add
+            float* scr = reinterpret_cast<float*>(smem);
+            if (lane == 0 && (et & 32) != 0) {             // second warp of each chunk group publishes
+#pragma unroll
+                for (int i = 0; i < 128; ++i) scr[cs_cg * 128 + i] = cs[i];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (lane == 0 && (et & 32) == 0) {
+                float* dst = job.cs_partial + (size_t)split * 256 + cs_cg * 128;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) dst[i] = cs[i] + scr[cs_cg * 128 + i];
+            }
         }
     }
     tc_fence_before();

@@ -15,6 +15,8 @@ struct DwJob {
     int n_pairs;
     int nw;                   // window width N (multiple of 16, <= 256)
     float* partial;           // [splits][256][nw] fp32
+    int colsum_pair;          // pair whose A-side tile is also column-summed (bias gradient), -1 = none
+    float* cs_partial;        // [splits][256] fp32
 };
 struct DwParams {
     int n_jobs;

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                 }
                 if (l == 7) {
                     // A operand of phase B's first GEMM: d_feat (scaled, fp16); also streamed for dW_8
-#pragma unroll 1
+#pragma unroll 4
                     for (int ch = 0; ch < 32; ++ch) {
                         float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
                         if (live && P.d_feat) {
