@@ -59,9 +59,10 @@ RNB_API int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float*
 
 /* SDFNetwork.forward + SDFNetwork.gradient fused (reference models/fields.py:82-127; call site
  * models/renderer.py:492-498).  Writes sdf [n], grad [n,3], the feature stream (fp16 [Npad x 256]) and the
- * activation streams the backward needs.  out_full (optional, may be NULL): fp32 [n,257] like the reference. */
+ * activation streams the backward needs: st_in0 [Npad x 64] (layer-0 input), st_in = 8 streams a_l [Npad x 256],
+ * st_w = 8 streams w_l = softplus'(z_l) * (dx-chain cotangent).  out_full (optional, may be NULL): fp32 [n,257] like the reference. */
 RNB_API int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* aux, float* out_sdf, float* out_grad,
-                     float* out_full, void* st_feat, void* st_in0, void* st_in, void* st_s, void* st_w, void* stream);
+                     float* out_full, void* st_feat, void* st_in0, void* st_in, void* st_w, void* stream);
 
 /* Double-backward of (sdf, features, gradient) w.r.t. the effective weights (what loss.backward() does to
  * SDFNetwork.forward + .gradient in the reference: exp_runner.py:261 through models/fields.py:82-127).
@@ -71,7 +72,7 @@ RNB_API int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const f
  * 217x256, 256x256 x4, 257x256), db[l] [out_l]; overwritten. */
 RNB_API size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts);
 RNB_API int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
-                const float* d_feat, const void* st_in0, const void* st_in, const void* st_s, const void* st_w,
+                const float* d_feat, const void* st_in0, const void* st_in, const void* st_w,
                 void* scratch, float* const* dW, float* const* db, void* stream);
 
 

@@ -180,7 +180,7 @@ int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float* aux, fl
 }
 
 int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* aux, float* out_sdf, float* out_grad,
-                     float* out_full, void* st_feat, void* st_in0, void* st_in, void* st_s, void* st_w, void* stream) {
+                     float* out_full, void* st_feat, void* st_in0, void* st_in, void* st_w, void* stream) {
     SdfFwdGradParams P{};
     P.src = to_src(pts);
     P.n_tiles = n_tiles(pts->n_pts);
@@ -190,12 +190,12 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
     add_step(P.tab, SDFW_F8, 256, 256);
     {
         const size_t SS = rnb_stream_bytes(pts->n_pts, 256);
-        for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256, 0, (const uint8_t*)st_s + (size_t)(l - 1) * SS);
+        for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256, 0, (const uint8_t*)st_in + (size_t)(l - 1) * SS);
     }
     add_step(P.tab, sdfw_tr(0), 64, 256);
     P.out_sdf = out_sdf; P.out_grad = out_grad; P.out_full = out_full;
     P.st_feat = (uint8_t*)st_feat; P.st_in0 = (uint8_t*)st_in0; P.st_in = (uint8_t*)st_in;
-    P.st_s = (uint8_t*)st_s; P.st_w = (uint8_t*)st_w;
+    P.st_w = (uint8_t*)st_w;
     P.stream_stride = rnb_stream_bytes(pts->n_pts, 256);
     return (int)profiled(T_SDF_FWD_GRAD, (cudaStream_t)stream, [&] { return launch_sdf_fwd_grad(P, sm_count(), (cudaStream_t)stream); });
 }
@@ -204,7 +204,7 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
 size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts) { return sdf_bwd_scratch(n_pts).total; }
 
 int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
-                const float* d_feat, const void* st_in0, const void* st_in, const void* st_s, const void* st_w,
+                const float* d_feat, const void* st_in0, const void* st_in, const void* st_w,
                 void* scratch, float* const* dW, float* const* db, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = pts->n_pts;
@@ -227,7 +227,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     add_step(P.tab, SDFW_T8, 256, 256);
     for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256);
     P.d_sdf = d_sdf; P.d_grad = d_grad; P.d_feat = d_feat; P.cot_absmax = absmax;
-    P.st_s = (const uint8_t*)st_s; P.st_w = (const uint8_t*)st_w;
+    P.st_in = (const uint8_t*)st_in; P.st_w = (const uint8_t*)st_w;
     P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_z2 = sc + L.z2; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;
     P.stream_stride = SS;
     e = profiled(T_SDF_BWD_DATA, st, [&] { return launch_sdf_bwd_data(P, sm_count(), st); });

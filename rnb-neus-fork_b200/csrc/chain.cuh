@@ -238,4 +238,8 @@ __device__ __forceinline__ void softplus100_ds(float z, float& a, float& s) {
     s = t >= 0.f ? r : e * r;
 }
 
+// softplus'(z) recovered from a = softplus(z):  a = log(1 + e^{100 z}) / 100  =>  sigmoid(100 z) = 1 - e^{-100 a}.
+// Lets the backward kernels read the activation stream they need anyway instead of a separate s stream.
+__device__ __forceinline__ float sig_from_a(float a) { return 1.f - ex2_approx(-144.26950408889634f * a); }
+
 }  // namespace rnb

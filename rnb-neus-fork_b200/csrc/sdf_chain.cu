@@ -60,13 +60,13 @@ __device__ __forceinline__ float fwd_layer_plain(const Epi& ep, const float* bia
 }
 
 // overwrite columns 217..255 of the A operand (and optionally a global stream) with 39 values
-template <class F>
+template <bool WRITE_A = true, class F>
 __device__ __forceinline__ void write_skip_cols(const Epi& ep, F&& val, uint8_t* stream, int64_t p) {
     // chunk 27 holds columns 216..223: keep column 216
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const __half h = __float2half_rn(val(i));
-        ep.st_a_half(SKIP_COL + i, h);
+        if (WRITE_A) ep.st_a_half(SKIP_COL + i, h);
         if (stream) *reinterpret_cast<__half*>(stream + stream_off(p, 27, 32) + (1 + i) * 2) = h;
     }
 #pragma unroll
@@ -75,7 +75,7 @@ __device__ __forceinline__ void write_skip_cols(const Epi& ep, F&& val, uint8_t*
         uint4 h;
         h.x = pack_h2(val(i0 + 0), val(i0 + 1)); h.y = pack_h2(val(i0 + 2), val(i0 + 3));
         h.z = pack_h2(val(i0 + 4), val(i0 + 5)); h.w = pack_h2(val(i0 + 6), val(i0 + 7));
-        ep.st_a(c, h);
+        if (WRITE_A) ep.st_a(c, h);
         if (stream) st_stream(stream, p, c, 32, h);
     }
 }
@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             for (int l = 0; l < 8; ++l) {
                 ep.wait_acc();
                 uint8_t* st_a_next = P.st_in + (size_t)l * SS;       // in_{l+1} = a_l
-                uint8_t* st_s = P.st_s + (size_t)l * SS;
                 const float* bl = bias + l * 256;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 256; c0 += 32) {
@@ -187,31 +186,23 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         float bb[8], ww[8];
                         load_bias8(bl + c0 + q * 8, bb);
                         if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
-                        float a[8], sg[8];
+                        float a[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            softplus100_ds(__uint_as_float(v[q * 8 + j]) + bb[j], a[j], sg[j]);
+                            a[j] = softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]);
                             if (l == 7) sdf = fmaf(a[j], ww[j], sdf);
                         }
-                        uint4 ha, hs;
+                        uint4 ha;
                         ha.x = pack_h2(a[0], a[1]); ha.y = pack_h2(a[2], a[3]); ha.z = pack_h2(a[4], a[5]); ha.w = pack_h2(a[6], a[7]);
-                        hs.x = pack_h2(sg[0], sg[1]); hs.y = pack_h2(sg[2], sg[3]); hs.z = pack_h2(sg[4], sg[5]); hs.w = pack_h2(sg[6], sg[7]);
                         const int ch = (c0 >> 3) + q;
                         ep.st_a(ch, ha);
                         st_stream(st_a_next, p, ch, 32, ha);
-                        st_stream(st_s, p, ch, 32, hs);
                     }
                 }
                 if (l == 3) {
                     float e[39];
                     pe_embed<6>(x, sc, e);
                     write_skip_cols(ep, [&](int i) { return e[i]; }, st_a_next, p);
-                    // s_3 = 0 on the skip columns, so w_3 = 0 there in the dx-chain and in K3
-                    uint8_t* z = st_s + stream_off(p, 27, 32);
-#pragma unroll
-                    for (int i = 1; i < 8; ++i) *reinterpret_cast<__half*>(z + i * 2) = __float2half_rn(0.f);
-#pragma unroll
-                    for (int c = 28; c < 32; ++c) st_stream(st_s, p, c, 32, make_uint4(0, 0, 0, 0));
                 }
                 ep.signal();
             }
@@ -221,7 +212,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             ep.wait_acc();
             {
                 const float* b8f = bias + 8 * 256;
-                const uint8_t* st_s7 = P.st_s + (size_t)7 * SS;
                 uint8_t* st_w7 = P.st_w + (size_t)7 * SS;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 256; c0 += 32) {
@@ -244,11 +234,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
 #pragma unroll
                             for (int j = 0; j < 8; ++j) o[j] = f[j];
                         }
-                        const uint4 hs = ld_stream(st_s7, p, ch, 32);
-                        const float2 s0 = unpack_h2(hs.x), s1 = unpack_h2(hs.y), s2 = unpack_h2(hs.z), s3 = unpack_h2(hs.w);
+                        // a_7 is still in the A operand buffer (this GEMM just consumed it): s_7 = 1 - exp(-100 a_7)
+                        const uint4 ha7 = *reinterpret_cast<const uint4*>(ep.sA + ((size_t)ch * TILE_M + ep.row) * 16);
+                        const float2 s0 = unpack_h2(ha7.x), s1 = unpack_h2(ha7.y), s2 = unpack_h2(ha7.z), s3 = unpack_h2(ha7.w);
                         uint4 hw;
-                        hw.x = pack_h2(s0.x * ww[0], s0.y * ww[1]); hw.y = pack_h2(s1.x * ww[2], s1.y * ww[3]);
-                        hw.z = pack_h2(s2.x * ww[4], s2.y * ww[5]); hw.w = pack_h2(s3.x * ww[6], s3.y * ww[7]);
+                        hw.x = pack_h2(sig_from_a(s0.x) * ww[0], sig_from_a(s0.y) * ww[1]);
+                        hw.y = pack_h2(sig_from_a(s1.x) * ww[2], sig_from_a(s1.y) * ww[3]);
+                        hw.z = pack_h2(sig_from_a(s2.x) * ww[4], sig_from_a(s2.y) * ww[5]);
+                        hw.w = pack_h2(sig_from_a(s3.x) * ww[6], sig_from_a(s3.y) * ww[7]);
                         ep.st_a(ch, hw);
                         st_stream(st_w7, p, ch, 32, hw);
                     }
@@ -260,7 +253,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             float g[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int l = 7; l >= 1; --l) {
-                const uint8_t* st_sp = P.st_s + (size_t)(l - 1) * SS;
+                const uint8_t* st_sp = P.st_in + (size_t)(l - 1) * SS;      // a_{l-1}; s_{l-1} = 1 - exp(-100 a)
                 uint8_t* st_wp = P.st_w + (size_t)(l - 1) * SS;
                 uint4 hs_n[4];
 #pragma unroll
@@ -286,13 +279,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
 #pragma unroll
                         for (int j = 0; j < 8; ++j) u[j] = __uint_as_float(v[q * 8 + j]);
                         uint4 hw;
-                        hw.x = pack_h2(s0.x * u[0], s0.y * u[1]); hw.y = pack_h2(s1.x * u[2], s1.y * u[3]);
-                        hw.z = pack_h2(s2.x * u[4], s2.y * u[5]); hw.w = pack_h2(s3.x * u[6], s3.y * u[7]);
+                        hw.x = pack_h2(sig_from_a(s0.x) * u[0], sig_from_a(s0.y) * u[1]);
+                        hw.y = pack_h2(sig_from_a(s1.x) * u[2], sig_from_a(s1.y) * u[3]);
+                        hw.z = pack_h2(sig_from_a(s2.x) * u[4], sig_from_a(s2.y) * u[5]);
+                        hw.w = pack_h2(sig_from_a(s3.x) * u[6], sig_from_a(s3.y) * u[7]);
                         ep.st_a(ch, hw);
                         st_stream(st_wp, p, ch, 32, hw);
                     }
                 }
                 if (l == 4) {
+                    // columns 217..255 of layer 4's input are the PE, not activations: w_3 = 0 there
+                    write_skip_cols(ep, [](int) { return 0.f; }, st_wp, p);
                     // uin_4[217:] is d sdf / d e through the skip connection: fold it into the gradient now
                     uint32_t v[32];
                     ep.ld_acc(192, v);
@@ -373,7 +370,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
             // ---------------- phase A, l = 0..7:  wbar = W_l uin_l ;  z2_l = 100(1-s)w*wbar ;  ua_bar = s*wbar
 #pragma unroll 1
             for (int l = 0; l < 8; ++l) {
-                const uint8_t* st_s = P.st_s + (size_t)l * SS;
+                const uint8_t* st_s = P.st_in + (size_t)l * SS;      // a_l; s_l = 1 - exp(-100 a_l)
                 const uint8_t* st_w = P.st_w + (size_t)l * SS;
                 uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
                 uint8_t* st_un = P.st_uin + (size_t)l * SS;          // uin_{l+1} = ua_bar_l
@@ -404,7 +401,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                         uint32_t z2[4], ub[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 sv = unpack_h2(hsa[j]), wv = unpack_h2(hwa[j]);
+                            const float2 av = unpack_h2(hsa[j]), wv = unpack_h2(hwa[j]);
+                            const float2 sv = make_float2(sig_from_a(av.x), sig_from_a(av.y));
                             const float wb0 = __uint_as_float(v[q * 8 + 2 * j]), wb1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
                             z2[j] = pack_h2_sat(100.f * (1.f - sv.x) * wv.x * wb0, 100.f * (1.f - sv.y) * wv.y * wb1);
                             ub[j] = pack_h2_sat(sv.x * wb0, sv.y * wb1);
@@ -422,6 +420,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
 #pragma unroll
                     for (int i = 0; i < 39; ++i) e[i] = pe_jvp_col<6>(i, sc, gb);
                     write_skip_cols(ep, [&](int i) { return fminf(fmaxf(e[i], -65504.f), 65504.f); }, st_un, p);
+                    write_skip_cols<false>(ep, [](int) { return 0.f; }, st_z2, p);     // no activation there: z2_3 = 0
                 }
                 if (l == 7) {
                     // A operand of phase B's first GEMM: d_feat (scaled, fp16); also streamed for dW_8
@@ -445,7 +444,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
             // ---------------- phase B: GEMM yields abar_l (l = 7..0);  zbar_l = s_l*abar_l + z2_l
 #pragma unroll 1
             for (int l = 7; l >= 0; --l) {
-                const uint8_t* st_s = P.st_s + (size_t)l * SS;
+                const uint8_t* st_s = P.st_in + (size_t)l * SS;      // a_l
                 const uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
                 uint8_t* st_zb = P.st_zbar + (size_t)l * SS;
                 uint4 hs_n[4], hz_n[4];
@@ -477,7 +476,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                         uint32_t zb[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 sv = unpack_h2(hsa[j]), zv = unpack_h2(hza[j]);
+                            const float2 av = unpack_h2(hsa[j]), zv = unpack_h2(hza[j]);
+                            const float2 sv = make_float2(sig_from_a(av.x), sig_from_a(av.y));
                             float a0 = __uint_as_float(v[q * 8 + 2 * j]), a1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
                             if (l == 7) {   // abar_7 = d_feat W_8[1:,:] + d_sdf W_8[0,:]
                                 a0 = fmaf(dsdf, ww[2 * j], a0);
@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                         if (l > 0) ep.st_a(ch, uz);
                     }
                 }
+                if (l == 3) write_skip_cols(ep, [](int) { return 0.f; }, st_zb, p);    // zbar_3 = 0 on the PE columns
                 if (l > 0) ep.signal();
             }
         }

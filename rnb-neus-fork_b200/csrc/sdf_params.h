@@ -45,7 +45,6 @@ struct SdfFwdGradParams {
     uint8_t* st_feat;          // fp16 stream [Npad x 256]
     uint8_t* st_in0;           // fp16 stream [Npad x 64]   layer-0 input
     uint8_t* st_in;            // 8 fp16 streams, index l = in_{l+1} = a_l
-    uint8_t* st_s;             // 8 fp16 streams, s_l = softplus'(z_l)
     uint8_t* st_w;             // 8 fp16 streams, w_l = s_l * ua_l
     size_t stream_stride;      // bytes of one 256-wide stream = Npad * 512
 };
@@ -60,7 +59,7 @@ struct SdfBwdParams {
     const float* d_grad;       // [n_pts,3]
     const float* d_feat;       // [n_pts,256] fp32 row-major
     const float* cot_absmax;   // device scalar: max |cotangent| over the three inputs
-    const uint8_t* st_s;
+    const uint8_t* st_in;      // 8 streams a_l (softplus' is recovered from them)
     const uint8_t* st_w;
     uint8_t* st_uin0;          // fp16 stream [Npad x 64]    uin_0 (scaled)
     uint8_t* st_uin;           // 8 streams, index l = uin_{l+1} = ua_bar_l (scaled)

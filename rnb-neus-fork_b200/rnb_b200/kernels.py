@@ -99,7 +99,6 @@ class SdfStreams:
         self.feat = torch.empty(s256, **u8)
         self.in0 = torch.empty(s64, **u8)
         self.inl = torch.empty(8 * s256, **u8)
-        self.s = torch.empty(8 * s256, **u8)
         self.w = torch.empty(8 * s256, **u8)
 
 
@@ -113,7 +112,7 @@ def sdf_fwd_grad(packed: SdfPacked, pts, streams: SdfStreams = None, want_full=F
     full = torch.empty(n, 257, dtype=torch.float32, device=dev) if want_full else None
     L.check(L.load().rnb_sdf_fwd_grad(C.byref(pts), L.ptr(packed.wblob), L.ptr(packed.aux), L.ptr(sdf), L.ptr(grad),
                                       L.ptr(full), L.ptr(streams.feat), L.ptr(streams.in0), L.ptr(streams.inl),
-                                      L.ptr(streams.s), L.ptr(streams.w), L.stream_ptr()), "sdf_fwd_grad")
+                                      L.ptr(streams.w), L.stream_ptr()), "sdf_fwd_grad")
     return sdf, grad, full, streams
 
 
@@ -137,7 +136,7 @@ def sdf_bwd(packed: SdfPacked, pts, streams: SdfStreams, d_sdf, d_grad, d_feat=N
     wp = (C.c_void_p * N_SDF_LAYERS)(*[L.ptr(t) for t in dWs])
     bp = (C.c_void_p * N_SDF_LAYERS)(*[L.ptr(t) for t in dbs])
     L.check(lib.rnb_sdf_bwd(C.byref(pts), L.ptr(packed.wblob), L.ptr(packed.aux), L.ptr(d_sdf), L.ptr(d_grad),
-                            L.ptr(d_feat), L.ptr(streams.in0), L.ptr(streams.inl), L.ptr(streams.s), L.ptr(streams.w),
+                            L.ptr(d_feat), L.ptr(streams.in0), L.ptr(streams.inl), L.ptr(streams.w),
                             L.ptr(scratch), wp, bp, L.stream_ptr()), "sdf_bwd")
     return dWs, dbs, scratch
 

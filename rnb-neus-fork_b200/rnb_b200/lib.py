@@ -54,7 +54,7 @@ _SIGNATURES = {
     "rnb_stream_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "rnb_sdf_pack": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP), _VP, _VP, _VP]),
     "rnb_sdf_fwd": (C.c_int, [C.POINTER(Points), _VP, _VP, _VP, C.c_float, _VP]),
-    "rnb_sdf_fwd_grad": (C.c_int, [C.POINTER(Points)] + [_VP] * 11),
+    "rnb_sdf_fwd_grad": (C.c_int, [C.POINTER(Points)] + [_VP] * 10),
     "rnb_sdf_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "rnb_albedo_wblob_bytes": (C.c_size_t, []),
     "rnb_albedo_aux_floats": (C.c_size_t, []),
@@ -71,7 +71,7 @@ _SIGNATURES = {
     "rnb_final_merge": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
     "rnb_composite_fwd": (C.c_int, [C.POINTER(Composite), _VP]),
     "rnb_composite_bwd": (C.c_int, [C.POINTER(Composite), _VP]),
-    "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 10 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
+    "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 9 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
 }
 
 
