@@ -288,7 +288,7 @@ def main():
         no_albedo = wl["no_albedo"]
         params = list(sdf.parameters()) + list(var.parameters()) + ([] if no_albedo else list(col.parameters()))
         red = FlatGradAllReducer(params)
-        opt = torch.optim.Adam(params, lr=5e-4)
+        opt = torch.optim.Adam(params, lr=5e-4, fused=True)
         host_b = [{k: v.pin_memory() for k, v in synth.make_batch(B, 3, True, 1 + rank, view=i).items()} for i in range(4)]
         dev_b = [{k: v.to(dev) for k, v in hb.items()} for hb in host_b]
         keys = ("rays_o", "rays_d", "near", "far", "lights_dir", "true_rgb", "mask")
