@@ -27,6 +27,18 @@ __device__ __forceinline__ void build_pe64(const float (&x)[3], const float (&nr
     for (int i = 0; i < 32; ++i) h[i] = pack_h2(e[2 * i], e[2 * i + 1]);
 }
 
+// A[:, 0:64] <- [PE4(point) | PE4(normal)] (half-0 threads)
+__device__ __noinline__ void emit_pe64(const Epi& ep, const float (&x)[3], const float (&nr)[3], uint8_t* stream, int64_t p) {
+    uint32_t h[32];
+    build_pe64(x, nr, h);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 u = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+        ep.st_a(c, u);
+        st_stream(stream, p, c, 8, u);
+    }
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __grid_constant__ AlbedoFwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const ChainSmem s = chain_carve(smem, ALB_A_COLS);
@@ -43,37 +55,28 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
         const float* b0 = P.aux + ALBX_B0;
         const float* b1 = P.aux + ALBX_B1;
         const float* w2 = P.aux + ALBX_W2;
+        const int ch0 = ep.col0 >> 3;
         for (int t = 0; t < n_my; ++t) {
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
             const bool live = p < P.src.n_pts;
             // A <- feature tile (already fp16, chunked)
 #pragma unroll 8
-            for (int ch = 0; ch < 32; ++ch) ep.st_a(ch, ld_stream(P.st_feat, p, ch, 32));
+            for (int k = 0; k < 16; ++k) ep.st_a(ch0 + k, ld_stream(P.st_feat, p, ch0 + k, 32));
             ep.signal();
             // step 0a done (features consumed): A[:, 0:64] <- positional encodings
             ep.wait_acc();
-            {
+            if (ep.half == 0) {
                 float x[3], nr[3] = {0.f, 0.f, 0.f};
                 load_point(P.src, p, x);
                 if (live) { nr[0] = __ldg(P.normals + p * 3); nr[1] = __ldg(P.normals + p * 3 + 1); nr[2] = __ldg(P.normals + p * 3 + 2); }
-                uint32_t h[32];
-                build_pe64(x, nr, h);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 u = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
-                    ep.st_a(c, u);
-                    st_stream(P.st_pe, p, c, 8, u);
-                }
+                emit_pe64(ep, x, nr, P.st_pe, p);
             }
             ep.signal();
             // step 0b: h0 = relu(z0 + b0)
             ep.wait_acc();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t v[32];
-                ep.ld_acc(c0, v);
+            ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     float bb[8], a[8];
                     load_bias8(b0 + c0 + q * 8, bb);
 #pragma unroll
@@ -83,17 +86,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
                     ep.st_a((c0 >> 3) + q, h);
                     st_stream(P.st_h0, p, (c0 >> 3) + q, 32, h);
                 }
-            }
+            });
             ep.signal();
             // step 1: h1 = relu(z1 + b1); albedo = sigmoid(W2 h1 + b2)
             ep.wait_acc();
             float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t v[32];
-                ep.ld_acc(c0, v);
+            ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     float bb[8], a[8], w[8];
                     load_bias8(b1 + c0 + q * 8, bb);
 #pragma unroll
@@ -108,11 +108,19 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
                     h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
                     st_stream(P.st_h1, p, (c0 >> 3) + q, 32, h);
                 }
+            });
+            // the two column halves of a row combine their partial dot products through the dead A buffer
+            if (ep.half == 1) {
+                float* xc = ep.xchg();
+                xc[0] = o[0]; xc[1] = o[1]; xc[2] = o[2];
             }
-            if (live) {
+            ep.sync_epi();
+            if (ep.half == 0 && live) {
+                const float* xc = ep.xchg();
 #pragma unroll
-                for (int k = 0; k < 3; ++k) P.albedo[p * 3 + k] = 1.f / (1.f + expf(-(o[k] + __ldg(P.aux + ALBX_B2 + k))));
+                for (int k = 0; k < 3; ++k) P.albedo[p * 3 + k] = 1.f / (1.f + expf(-(o[k] + xc[k] + __ldg(P.aux + ALBX_B2 + k))));
             }
+            // all reads of the exchange slots precede the next tile's writes of chunk 8 by the same thread
         }
     }
     chain_teardown(s, tmem);
@@ -134,6 +142,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
         const float* w2 = P.aux + ALBX_W2;
         const float scale = cot_scale_from_max(__ldg(P.cot_absmax));
         const float inv_scale = 1.f / scale;
+        const int ch0 = ep.col0 >> 3;
+        const int c_last = ep.col0 + EPI_HALF_COLS - 16;
         for (int t = 0; t < n_my; ++t) {
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
             const bool live = p < P.src.n_pts;
@@ -146,11 +156,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
                     dz2[k] = __ldg(P.d_albedo + p * 3 + k) * a * (1.f - a);
                 }
             }
+            if (ep.half == 0) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) P.dz2[(size_t)k * P.n_pad + p] = dz2[k];
+                for (int k = 0; k < 3; ++k) P.dz2[(size_t)k * P.n_pad + p] = dz2[k];
+            }
             // dz1 = (W2^T dz2) * (h1 > 0)
 #pragma unroll 4
-            for (int ch = 0; ch < 32; ++ch) {
+            for (int k = 0; k < 16; ++k) {
+                const int ch = ch0 + k;
                 const uint4 hh = ld_stream(P.st_h1, p, ch, 32);
                 const uint32_t ha[4] = {hh.x, hh.y, hh.z, hh.w};
                 float w0[8], w1[8], w2r[8];
@@ -174,23 +187,20 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
             ep.signal();
             // step B1: dh0 = dz1 W1 ; dz0 = dh0 * (h0 > 0)
             {
-                uint4 hh_n[4];
+                uint4 hh_n[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) hh_n[q] = ld_stream(P.st_h0, p, q, 32);
+                for (int q = 0; q < 2; ++q) hh_n[q] = ld_stream(P.st_h0, p, ch0 + q, 32);
                 ep.wait_acc();
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint4 hh_c[4];
+                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+                    uint4 hh_c[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) hh_c[q] = hh_n[q];
-                    if (c0 + 32 < 256) {
+                    for (int q = 0; q < 2; ++q) hh_c[q] = hh_n[q];
+                    if (c0 < c_last) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) hh_n[q] = ld_stream(P.st_h0, p, (c0 >> 3) + 4 + q, 32);
+                        for (int q = 0; q < 2; ++q) hh_n[q] = ld_stream(P.st_h0, p, (c0 >> 3) + 2 + q, 32);
                     }
-                    uint32_t v[32];
-                    ep.ld_acc(c0, v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int ch = (c0 >> 3) + q;
                         const uint4 hh = hh_c[q];
                         const uint32_t ha[4] = {hh.x, hh.y, hh.z, hh.w};
@@ -206,39 +216,39 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
                         ep.st_a(ch, u);
                         st_stream(P.st_dz0, p, ch, 32, u);
                     }
-                }
+                });
             }
             ep.signal();
             // step B0a: d_feat = dz0 W0[:, feat]   -> fp32 [n,256] (input of the SDF backward)
             ep.wait_acc();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t v[32];
-                ep.ld_acc(c0, v);
+            ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
                 if (live) {
                     float4* dst = reinterpret_cast<float4*>(P.d_feat + (size_t)p * 256 + c0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
+                    for (int j = 0; j < 4; ++j)
                         dst[j] = make_float4(__uint_as_float(v[4 * j]) * inv_scale, __uint_as_float(v[4 * j + 1]) * inv_scale,
                                              __uint_as_float(v[4 * j + 2]) * inv_scale, __uint_as_float(v[4 * j + 3]) * inv_scale);
                 }
-            }
+            });
             ep.signal();       // A (dz0) is reused unchanged by the next GEMM
             // step B0b (N = 64): d_pe = dz0 W0[:, pe] ; d_normal = J_4(normal)^T d_pe[27:54]
             ep.wait_acc();
-            {
+            if (ep.half == 0) {
                 float nr[3] = {0.f, 0.f, 0.f};
                 if (live) { nr[0] = __ldg(P.normals + p * 3); nr[1] = __ldg(P.normals + p * 3 + 1); nr[2] = __ldg(P.normals + p * 3 + 2); }
                 SinCos<4> sn;
                 sn.compute(nr[0], nr[1], nr[2]);
                 float g[3] = {0.f, 0.f, 0.f};
-                uint32_t v[32];
-                ep.ld_acc(0, v);
+                uint32_t v[16];
+                ep.ld_acc16(16, v);
 #pragma unroll
-                for (int j = 27; j < 32; ++j) pe_vjp_col<4>(j - 27, sn, __uint_as_float(v[j]), g);
-                ep.ld_acc(32, v);
+                for (int j = 11; j < 16; ++j) pe_vjp_col<4>(16 + j - 27, sn, __uint_as_float(v[j]), g);
+                ep.ld_acc16(32, v);
 #pragma unroll
-                for (int j = 0; j < 22; ++j) pe_vjp_col<4>(32 + j - 27, sn, __uint_as_float(v[j]), g);
+                for (int j = 0; j < 16; ++j) pe_vjp_col<4>(32 + j - 27, sn, __uint_as_float(v[j]), g);
+                ep.ld_acc16(48, v);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) pe_vjp_col<4>(48 + j - 27, sn, __uint_as_float(v[j]), g);
                 if (live) {
                     P.d_normal[p * 3 + 0] = g[0] * inv_scale;
                     P.d_normal[p * 3 + 1] = g[1] * inv_scale;

@@ -1,12 +1,15 @@
 // Tile-major MLP chain machinery shared by the SDF / albedo / NeRF kernels.
 //
-// One CTA = 6 warps = 192 threads, two CTAs co-resident per SM (112 KB smem + 256 TMEM columns each), so one
+// One CTA = 10 warps = 320 threads, two CTAs co-resident per SM (112 KB smem + 256 TMEM columns each), so one
 // CTA's tcgen05.mma phase overlaps the other's epilogue without explicit ping-pong code.
 //   warp 0   : weight producer  -- cp.async.bulk (UBLKCP) of pre-packed K=32 weight slices into a 3-slot ring
 //   warp 1   : MMA issuer       -- lane 0 issues tcgen05.mma (M=128, N<=256, K=16) from smem A x smem W into TMEM
-//   warps 2-5: epilogue         -- one thread per point row: tcgen05.ld the fp32 accumulator, bias + activation
-//                                  (+ derivative terms) in registers, write the next layer's A operand (fp16,
-//                                  "chunked" K-major image, see common.cuh) into smem and any streams to HBM.
+//   warps 2-9: epilogue         -- two threads per point row (TMEM lane), each owning one 128-column half of the
+//                                  accumulator: tcgen05.ld in 16-column chunks with the next chunk's load in flight,
+//                                  bias + activation (+ derivative terms) in registers, write the next layer's A
+//                                  operand (fp16, "chunked" K-major image, see common.cuh) into smem and any streams
+//                                  to HBM.  Eight epilogue warps per CTA = four per SM sub-partition with both CTAs
+//                                  resident: the thread-level parallelism that hides the TMEM / L2 latencies.
 // A "chain" is a table of GEMM steps executed strictly in order for each 128-point tile; step s+1's A operand
 // is written by step s's epilogue.
 #pragma once
@@ -17,7 +20,9 @@ namespace rnb {
 constexpr int TILE_M = 128;
 constexpr int RING_STAGES = 3;
 constexpr int STAGE_BYTES = 16384;        // K=32 slice of a 256-row operand
-constexpr int CHAIN_THREADS = 192;
+constexpr int CHAIN_THREADS = 320;
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_HALF_COLS = 128;     // accumulator columns owned by one epilogue thread
 constexpr int MAX_STEPS = 24;
 constexpr int TMEM_COLS = 256;
 
@@ -71,7 +76,7 @@ __device__ __forceinline__ uint32_t chain_setup(const ChainSmem& s) {
             mbar_init(&s.empty[i], 1);
         }
         mbar_init(s.acc_full, 1);
-        mbar_init(s.a_ready, TILE_M);
+        mbar_init(s.a_ready, EPI_THREADS);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(s.tmem_slot, TMEM_COLS);
@@ -150,7 +155,7 @@ __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& 
     }
 }
 
-// per-thread epilogue context (warps 2..5)
+// per-thread epilogue context (warps 2..9)
 struct Epi {
     uint8_t* sA;
     uint64_t* acc_full;
@@ -158,6 +163,8 @@ struct Epi {
     uint32_t tmem_row;   // TMEM address of this warp's lane quadrant, column 0
     uint32_t acc_cnt;
     int row;             // 0..127 = TMEM lane = point row inside the tile
+    int half;            // 0: accumulator columns 0..127, 1: columns 128..255 (warp-uniform)
+    int col0;            // = half * 128
 
     __device__ __forceinline__ void init(const ChainSmem& s, uint32_t tmem) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,6 +174,8 @@ struct Epi {
         a_ready = s.a_ready;
         tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
         row = quad * 32 + lane;
+        half = (warp - 2) >> 2;
+        col0 = half * EPI_HALF_COLS;
         acc_cnt = 0;
     }
     __device__ __forceinline__ void wait_acc() {
@@ -180,16 +189,52 @@ struct Epi {
         fence_proxy_async();
         mbar_arrive(a_ready);
     }
+    // rendezvous of the 256 epilogue threads (named barrier 1; warps 0/1 never join)
+    __device__ __forceinline__ void sync_epi() const { asm volatile("bar.sync 1, 256;" ::: "memory"); }
     __device__ __forceinline__ void st_a(int chunk, uint4 v) const {
         *reinterpret_cast<uint4*>(sA + ((size_t)chunk * TILE_M + row) * 16) = v;
     }
+    __device__ __forceinline__ uint4 ld_a(int chunk) const {
+        return *reinterpret_cast<const uint4*>(sA + ((size_t)chunk * TILE_M + row) * 16);
+    }
     __device__ __forceinline__ void st_a_half(int col, __half h) const {
         *reinterpret_cast<__half*>(sA + ((size_t)(col >> 3) * TILE_M + row) * 16 + (col & 7) * 2) = h;
+    }
+    // Per-row exchange slot (4 floats) between the two threads of a row, inside the A buffer at this row's own
+    // 16 bytes of chunk 8 (a chunk of half 0).  Protocol: A must be dead (its GEMM completed, acc_full seen);
+    // the half-1 thread writes, sync_epi(), the half-0 thread reads -- and only afterwards overwrites chunk 8 in
+    // its own sweep, so one barrier suffices.
+    __device__ __forceinline__ float* xchg() const {
+        return reinterpret_cast<float*>(sA + ((size_t)8 * TILE_M + row) * 16);
     }
     __device__ __forceinline__ void ld_acc(int c0, uint32_t (&v)[32]) const {
         tmem_ld32(tmem_row + (uint32_t)c0, v);
         tmem_ld_wait();
     }
+    __device__ __forceinline__ void ld_acc16(int c0, uint32_t (&v)[16]) const {
+        tmem_ld16(tmem_row + (uint32_t)c0, v);
+        tmem_ld_wait16(v);
+    }
+    // Sweep NCH 16-column chunks starting at column c_begin: f(c, v) gets the first column of the chunk and its 16
+    // fp32 accumulator values (as bits).  The TMEM load of chunk i+1 is in flight while chunk i is processed.
+    template <int NCH = 8, class F>
+    __device__ __forceinline__ void sweep(int c_begin, F&& f) const {
+        static_assert(NCH % 2 == 0, "even chunk count");
+        uint32_t va[16], vb[16];
+        tmem_ld16(tmem_row + (uint32_t)c_begin, va);
+#pragma unroll 1
+        for (int i = 0; i < NCH / 2; ++i) {
+            const int c = c_begin + i * 32;
+            tmem_ld_wait16(va);
+            tmem_ld16(tmem_row + (uint32_t)(c + 16), vb);
+            f(c, va);
+            tmem_ld_wait16(vb);
+            if (i + 1 < NCH / 2) tmem_ld16(tmem_row + (uint32_t)(c + 32), va);
+            f(c + 16, vb);
+        }
+    }
+    template <class F>
+    __device__ __forceinline__ void sweep_half(F&& f) const { sweep<8>(col0, f); }
 };
 
 // ---- global "stream" images: [n_pts/64 subtiles][C/8 chunks][64 rows][16 B]  (data layout)

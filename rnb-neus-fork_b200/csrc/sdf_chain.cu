@@ -30,16 +30,14 @@ __device__ __forceinline__ void build_in0(const float (&x)[3], const SinCos<6>& 
 }
 
 // ======================================================================================= K1 / K8
-// One hidden layer's epilogue: z = acc + b, a = softplus(z) -> next A operand.  LAST also reduces the sdf row.
+// One hidden layer's epilogue over this thread's 128 columns: z = acc + b, a = softplus(z) -> next A operand.
+// LAST also reduces this half's part of the sdf row.
 template <bool LAST>
 __device__ __forceinline__ float fwd_layer_plain(const Epi& ep, const float* bias, const float* w8row) {
     float acc = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-        uint32_t v[32];
-        ep.ld_acc(c0, v);
+    ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
             float bb[8], ww[8];
             load_bias8(bias + c0 + q * 8, bb);
             if (LAST) load_bias8(w8row + c0 + q * 8, ww);
@@ -55,7 +53,7 @@ __device__ __forceinline__ float fwd_layer_plain(const Epi& ep, const float* bia
                 ep.st_a((c0 >> 3) + q, h);
             }
         }
-    }
+    });
     return acc;
 }
 
@@ -89,6 +87,23 @@ __device__ __forceinline__ void write_in0(const Epi& ep, const uint32_t (&h)[32]
     }
 }
 
+// layer-0 operand of a point (half-0 threads): PE + x_lo columns
+__device__ __noinline__ void emit_in0(const Epi& ep, const float (&x)[3], uint8_t* stream, int64_t p) {
+    SinCos<6> sc;
+    sc.compute(x[0], x[1], x[2]);
+    uint32_t h[32];
+    build_in0(x, sc, h);
+    write_in0(ep, h, stream, p);
+}
+// skip connection (half-1 threads): columns 217..255 of layer 4's input are the PE of the point
+__device__ __noinline__ void emit_skip_pe(const Epi& ep, const float (&x)[3], uint8_t* stream, int64_t p) {
+    SinCos<6> sc;
+    sc.compute(x[0], x[1], x[2]);
+    float e[39];
+    pe_embed<6>(x, sc, e);
+    write_skip_cols(ep, [&](int i) { return e[i]; }, stream, p);
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_kernel(const __grid_constant__ SdfFwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const ChainSmem s = chain_carve(smem, SDF_A_COLS);
@@ -109,31 +124,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_kernel(const __grid_
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
             float x[3];
             load_point(P.src, p, x);
-            SinCos<6> sc;
-            sc.compute(x[0], x[1], x[2]);
-            {
-                uint32_t h[32];
-                build_in0(x, sc, h);
-                write_in0(ep, h, nullptr, p);
-            }
+            if (ep.half == 0) emit_in0(ep, x, nullptr, p);
             ep.signal();
-            float sdf = 0.f;
+            float part = 0.f;
 #pragma unroll 1
             for (int l = 0; l < 8; ++l) {
                 ep.wait_acc();
                 if (l < 7) {
                     fwd_layer_plain<false>(ep, bias + l * 256, w8row);
-                    if (l == 3) {
-                        float e[39];
-                        pe_embed<6>(x, sc, e);
-                        write_skip_cols(ep, [&](int i) { return e[i]; }, nullptr, p);
-                    }
+                    if (l == 3 && ep.half == 1) emit_skip_pe(ep, x, nullptr, p);
                     ep.signal();
                 } else {
-                    sdf = fwd_layer_plain<true>(ep, bias + l * 256, w8row) + b8;
+                    part = fwd_layer_plain<true>(ep, bias + l * 256, w8row);
                 }
             }
-            if (p < P.src.n_pts) P.out[p] = P.out_scale * sdf;
+            // sdf = <a_7, W_8[0,:]> + b_8[0]: the two column halves of a row meet through the (now dead) A buffer
+            if (ep.half == 1) *ep.xchg() = part;
+            ep.sync_epi();
+            if (ep.half == 0 && p < P.src.n_pts) P.out[p] = P.out_scale * (part + *ep.xchg() + b8);
         }
     }
     chain_teardown(s, tmem);
@@ -155,34 +163,25 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
         ep.init(s, tmem);
         const float* bias = P.aux;
         const float* w8row = P.aux + AUX_W8ROW;
-        const float b8 = __ldg(P.aux + AUX_B8_0);
         const size_t SS = P.stream_stride;
+        const int c_last = ep.col0 + EPI_HALF_COLS - 16;
         for (int t = 0; t < n_my; ++t) {
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
             const bool live = p < P.src.n_pts;
             float x[3];
             load_point(P.src, p, x);
-            SinCos<6> sc;
-            sc.compute(x[0], x[1], x[2]);
-            {
-                uint32_t h[32];
-                build_in0(x, sc, h);
-                write_in0(ep, h, P.st_in0, p);
-            }
+            if (ep.half == 0) emit_in0(ep, x, P.st_in0, p);
             ep.signal();
-            // ---------------- forward, layers 0..7: a_l -> A and stream in_{l+1}; s_l -> stream
+            // ---------------- forward, layers 0..7: a_l -> A operand and stream in_{l+1}
             float sdf = 0.f;
 #pragma unroll 1
             for (int l = 0; l < 8; ++l) {
                 ep.wait_acc();
                 uint8_t* st_a_next = P.st_in + (size_t)l * SS;       // in_{l+1} = a_l
                 const float* bl = bias + l * 256;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint32_t v[32];
-                    ep.ld_acc(c0, v);
+                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         float bb[8], ww[8];
                         load_bias8(bl + c0 + q * 8, bb);
                         if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
@@ -198,27 +197,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         ep.st_a(ch, ha);
                         st_stream(st_a_next, p, ch, 32, ha);
                     }
-                }
-                if (l == 3) {
-                    float e[39];
-                    pe_embed<6>(x, sc, e);
-                    write_skip_cols(ep, [&](int i) { return e[i]; }, st_a_next, p);
-                }
+                });
+                if (l == 3 && ep.half == 1) emit_skip_pe(ep, x, st_a_next, p);
                 ep.signal();
             }
-            sdf += b8;
-            if (live) P.out_sdf[p] = sdf;
             // ---------------- layer 8 features; then seed the dx-chain: w_7 = s_7 * W_8[0,:]
             ep.wait_acc();
             {
                 const float* b8f = bias + 8 * 256;
                 uint8_t* st_w7 = P.st_w + (size_t)7 * SS;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint32_t v[32];
-                    ep.ld_acc(c0, v);
+                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         float bb[8], ww[8];
                         load_bias8(b8f + c0 + q * 8, bb);
                         load_bias8(w8row + c0 + q * 8, ww);
@@ -235,7 +225,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                             for (int j = 0; j < 8; ++j) o[j] = f[j];
                         }
                         // a_7 is still in the A operand buffer (this GEMM just consumed it): s_7 = 1 - exp(-100 a_7)
-                        const uint4 ha7 = *reinterpret_cast<const uint4*>(ep.sA + ((size_t)ch * TILE_M + ep.row) * 16);
+                        const uint4 ha7 = ep.ld_a(ch);
                         const float2 s0 = unpack_h2(ha7.x), s1 = unpack_h2(ha7.y), s2 = unpack_h2(ha7.z), s3 = unpack_h2(ha7.w);
                         uint4 hw;
                         hw.x = pack_h2(sig_from_a(s0.x) * ww[0], sig_from_a(s0.y) * ww[1]);
@@ -245,8 +235,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         ep.st_a(ch, hw);
                         st_stream(st_w7, p, ch, 32, hw);
                     }
-                }
-                if (P.out_full && live) P.out_full[(size_t)p * 257] = sdf;
+                });
             }
             ep.signal();
             // ---------------- dx-chain: GEMM l (= 7..1) yields ua_{l-1}; w_{l-1} = s_{l-1} * ua_{l-1}
@@ -255,23 +244,32 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             for (int l = 7; l >= 1; --l) {
                 const uint8_t* st_sp = P.st_in + (size_t)(l - 1) * SS;      // a_{l-1}; s_{l-1} = 1 - exp(-100 a)
                 uint8_t* st_wp = P.st_w + (size_t)(l - 1) * SS;
-                uint4 hs_n[4];
+                uint4 hs_n[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) hs_n[q] = ld_stream(st_sp, p, q, 32);
+                for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_sp, p, (ep.col0 >> 3) + q, 32);
                 ep.wait_acc();
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint4 hs_c[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) hs_c[q] = hs_n[q];
-                    if (c0 + 32 < 256) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) hs_n[q] = ld_stream(st_sp, p, (c0 >> 3) + 4 + q, 32);
+                if (l == 7) {
+                    // A (= w_7) is dead: the two halves of the row combine their parts of <a_7, W_8[0,:]>
+                    if (ep.half == 1) *ep.xchg() = sdf;
+                    ep.sync_epi();
+                    if (ep.half == 0) {
+                        sdf += *ep.xchg() + __ldg(P.aux + AUX_B8_0);
+                        if (live) {
+                            P.out_sdf[p] = sdf;
+                            if (P.out_full) P.out_full[(size_t)p * 257] = sdf;
+                        }
                     }
-                    uint32_t v[32];
-                    ep.ld_acc(c0, v);
+                }
+                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+                    uint4 hs_c[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) hs_c[q] = hs_n[q];
+                    if (c0 < c_last) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_sp, p, (c0 >> 3) + 2 + q, 32);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
                         const int ch = (c0 >> 3) + q;
                         const uint4 hs = hs_c[q];
                         const float2 s0 = unpack_h2(hs.x), s1 = unpack_h2(hs.y), s2 = unpack_h2(hs.z), s3 = unpack_h2(hs.w);
@@ -286,36 +284,49 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         ep.st_a(ch, hw);
                         st_stream(st_wp, p, ch, 32, hw);
                     }
-                }
+                });
                 if (l == 4) {
-                    // columns 217..255 of layer 4's input are the PE, not activations: w_3 = 0 there
-                    write_skip_cols(ep, [](int) { return 0.f; }, st_wp, p);
-                    // uin_4[217:] is d sdf / d e through the skip connection: fold it into the gradient now
-                    uint32_t v[32];
-                    ep.ld_acc(192, v);
+                    if (ep.half == 1) {
+                        // columns 217..255 of layer 4's input are the PE, not activations: w_3 = 0 there
+                        write_skip_cols(ep, [](int) { return 0.f; }, st_wp, p);
+                    } else {
+                        // uin_4[217:] is d sdf / d e through the skip connection: fold it into the gradient now
+                        SinCos<6> sc;
+                        sc.compute(x[0], x[1], x[2]);
+                        uint32_t v[16];
+                        ep.ld_acc16(208, v);
 #pragma unroll
-                    for (int j = SKIP_COL - 192; j < 32; ++j) pe_vjp_col<6>(192 + j - SKIP_COL, sc, __uint_as_float(v[j]), g);
-                    ep.ld_acc(224, v);
+                        for (int j = SKIP_COL - 208; j < 16; ++j) pe_vjp_col<6>(208 + j - SKIP_COL, sc, __uint_as_float(v[j]), g);
+                        ep.ld_acc16(224, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) pe_vjp_col<6>(224 + j - SKIP_COL, sc, __uint_as_float(v[j]), g);
+                        for (int j = 0; j < 16; ++j) pe_vjp_col<6>(224 + j - SKIP_COL, sc, __uint_as_float(v[j]), g);
+                        ep.ld_acc16(240, v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pe_vjp_col<6>(240 + j - SKIP_COL, sc, __uint_as_float(v[j]), g);
+                    }
                 }
                 ep.signal();
             }
             // ---------------- last dx GEMM (N = 64): uin_0 = d sdf / d e
             ep.wait_acc();
-            {
-                uint32_t v[32];
-                ep.ld_acc(0, v);
+            if (ep.half == 0) {
+                SinCos<6> sc;
+                sc.compute(x[0], x[1], x[2]);
+                uint32_t v[16];
+                ep.ld_acc16(0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) pe_vjp_col<6>(j, sc, __uint_as_float(v[j]), g);
-                ep.ld_acc(32, v);
+                for (int j = 0; j < 16; ++j) pe_vjp_col<6>(j, sc, __uint_as_float(v[j]), g);
+                ep.ld_acc16(16, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pe_vjp_col<6>(16 + j, sc, __uint_as_float(v[j]), g);
+                ep.ld_acc16(32, v);
 #pragma unroll
                 for (int j = 0; j < 7; ++j) pe_vjp_col<6>(32 + j, sc, __uint_as_float(v[j]), g);
-            }
-            if (live) {
-                P.out_grad[p * 3 + 0] = g[0];
-                P.out_grad[p * 3 + 1] = g[1];
-                P.out_grad[p * 3 + 2] = g[2];
+                if (live) {
+                    P.out_grad[p * 3 + 0] = g[0];
+                    P.out_grad[p * 3 + 1] = g[1];
+                    P.out_grad[p * 3 + 2] = g[2];
+                }
             }
             // the next tile's prologue signals; nothing to do here
         }
@@ -324,6 +335,29 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
 }
 
 // ======================================================================================= K3a
+// uin_0 = J_e gbar in the 64-wide layer-0 column layout (x_lo columns carry no cotangent); half-0 threads
+__device__ __noinline__ void emit_uin0(const Epi& ep, const float (&x)[3], const float (&gb)[3], uint8_t* stream, int64_t p) {
+    SinCos<6> sc;
+    sc.compute(x[0], x[1], x[2]);
+    uint32_t h[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float e0 = 2 * i < 39 ? pe_jvp_col<6>(2 * i, sc, gb) : 0.f;
+        const float e1 = 2 * i + 1 < 39 ? pe_jvp_col<6>(2 * i + 1, sc, gb) : 0.f;
+        h[i] = pack_h2_sat(e0, e1);
+    }
+    write_in0(ep, h, stream, p);
+}
+// uin_4 = cat[ua_bar_3, ebar] (the 1/sqrt2 lives in the packed W_4); half-1 threads
+__device__ __noinline__ void emit_skip_ebar(const Epi& ep, const float (&x)[3], const float (&gb)[3], uint8_t* stream, int64_t p) {
+    SinCos<6> sc;
+    sc.compute(x[0], x[1], x[2]);
+    float e[39];
+#pragma unroll
+    for (int i = 0; i < 39; ++i) e[i] = pe_jvp_col<6>(i, sc, gb);
+    write_skip_cols(ep, [&](int i) { return fminf(fmaxf(e[i], -65504.f), 65504.f); }, stream, p);
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __grid_constant__ SdfBwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const ChainSmem s = chain_carve(smem, SDF_A_COLS);
@@ -340,13 +374,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
         const float* w8row = P.aux + AUX_W8ROW;
         const size_t SS = P.stream_stride;
         const float scale = cot_scale_from_max(__ldg(P.cot_absmax));
+        const int c_last = ep.col0 + EPI_HALF_COLS - 16;
+        const int ch0 = ep.col0 >> 3;
         for (int t = 0; t < n_my; ++t) {
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
             const bool live = p < P.src.n_pts;
             float x[3];
             load_point(P.src, p, x);
-            SinCos<6> sc;
-            sc.compute(x[0], x[1], x[2]);
             float gb[3] = {0.f, 0.f, 0.f};
             float dsdf = 0.f;
             if (live) {
@@ -355,17 +389,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                 gb[2] = __ldg(P.d_grad + p * 3 + 2) * scale;
                 dsdf = __ldg(P.d_sdf + p) * scale;
             }
-            // uin_0 = J_e gbar in the 64-wide layer-0 column layout (x_lo columns carry no cotangent)
-            {
-                uint32_t h[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float e0 = 2 * i < 39 ? pe_jvp_col<6>(2 * i, sc, gb) : 0.f;
-                    const float e1 = 2 * i + 1 < 39 ? pe_jvp_col<6>(2 * i + 1, sc, gb) : 0.f;
-                    h[i] = pack_h2_sat(e0, e1);
-                }
-                write_in0(ep, h, P.st_uin0, p);
-            }
+            if (ep.half == 0) emit_uin0(ep, x, gb, P.st_uin0, p);
             ep.signal();
             // ---------------- phase A, l = 0..7:  wbar = W_l uin_l ;  z2_l = 100(1-s)w*wbar ;  ua_bar = s*wbar
 #pragma unroll 1
@@ -374,26 +398,23 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                 const uint8_t* st_w = P.st_w + (size_t)l * SS;
                 uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
                 uint8_t* st_un = P.st_uin + (size_t)l * SS;          // uin_{l+1} = ua_bar_l
-                uint4 hs_n[4], hw_n[4];
+                uint4 hs_n[2], hw_n[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { hs_n[q] = ld_stream(st_s, p, q, 32); hw_n[q] = ld_stream(st_w, p, q, 32); }
+                for (int q = 0; q < 2; ++q) { hs_n[q] = ld_stream(st_s, p, ch0 + q, 32); hw_n[q] = ld_stream(st_w, p, ch0 + q, 32); }
                 ep.wait_acc();
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint4 hs_c[4], hw_c[4];
+                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+                    uint4 hs_c[2], hw_c[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { hs_c[q] = hs_n[q]; hw_c[q] = hw_n[q]; }
-                    if (c0 + 32 < 256) {
+                    for (int q = 0; q < 2; ++q) { hs_c[q] = hs_n[q]; hw_c[q] = hw_n[q]; }
+                    if (c0 < c_last) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 4 + q, 32);
-                            hw_n[q] = ld_stream(st_w, p, (c0 >> 3) + 4 + q, 32);
+                        for (int q = 0; q < 2; ++q) {
+                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 2 + q, 32);
+                            hw_n[q] = ld_stream(st_w, p, (c0 >> 3) + 2 + q, 32);
                         }
                     }
-                    uint32_t v[32];
-                    ep.ld_acc(c0, v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int ch = (c0 >> 3) + q;
                         const uint4 hs = hs_c[q];
                         const uint4 hw = hw_c[q];
@@ -402,10 +423,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float2 av = unpack_h2(hsa[j]), wv = unpack_h2(hwa[j]);
-                            const float2 sv = make_float2(sig_from_a(av.x), sig_from_a(av.y));
+                            // e100 = 100 (1 - s) = 100 exp(-100 a);  s = 1 - e100 / 100
+                            const float e0 = ex2_approx(fmaf(-144.26950408889634f, av.x, 6.643856189774724f));
+                            const float e1 = ex2_approx(fmaf(-144.26950408889634f, av.y, 6.643856189774724f));
                             const float wb0 = __uint_as_float(v[q * 8 + 2 * j]), wb1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
-                            z2[j] = pack_h2_sat(100.f * (1.f - sv.x) * wv.x * wb0, 100.f * (1.f - sv.y) * wv.y * wb1);
-                            ub[j] = pack_h2_sat(sv.x * wb0, sv.y * wb1);
+                            z2[j] = pack_h2_sat(e0 * wv.x * wb0, e1 * wv.y * wb1);
+                            ub[j] = pack_h2_sat(fmaf(-0.01f * e0, wb0, wb0), fmaf(-0.01f * e1, wb1, wb1));
                         }
                         const uint4 uz = make_uint4(z2[0], z2[1], z2[2], z2[3]);
                         const uint4 uu = make_uint4(ub[0], ub[1], ub[2], ub[3]);
@@ -413,19 +436,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                         st_stream(st_un, p, ch, 32, uu);
                         if (l < 7) ep.st_a(ch, uu);
                     }
-                }
-                if (l == 3) {
-                    // uin_4 = cat[ua_bar_3, ebar]  (the 1/sqrt2 lives in the packed W_4)
-                    float e[39];
-#pragma unroll
-                    for (int i = 0; i < 39; ++i) e[i] = pe_jvp_col<6>(i, sc, gb);
-                    write_skip_cols(ep, [&](int i) { return fminf(fmaxf(e[i], -65504.f), 65504.f); }, st_un, p);
+                });
+                if (l == 3 && ep.half == 1) {
+                    emit_skip_ebar(ep, x, gb, st_un, p);
                     write_skip_cols<false>(ep, [](int) { return 0.f; }, st_z2, p);     // no activation there: z2_3 = 0
                 }
                 if (l == 7) {
                     // A operand of phase B's first GEMM: d_feat (scaled, fp16); also streamed for dW_8
 #pragma unroll 4
-                    for (int ch = 0; ch < 32; ++ch) {
+                    for (int k = 0; k < 16; ++k) {
+                        const int ch = ch0 + k;
                         float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
                         if (live && P.d_feat) {
                             const float4* src = reinterpret_cast<const float4*>(P.d_feat + (size_t)p * 256 + ch * 8);
@@ -447,26 +467,23 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                 const uint8_t* st_s = P.st_in + (size_t)l * SS;      // a_l
                 const uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
                 uint8_t* st_zb = P.st_zbar + (size_t)l * SS;
-                uint4 hs_n[4], hz_n[4];
+                uint4 hs_n[2], hz_n[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { hs_n[q] = ld_stream(st_s, p, q, 32); hz_n[q] = ld_stream(st_z2, p, q, 32); }
+                for (int q = 0; q < 2; ++q) { hs_n[q] = ld_stream(st_s, p, ch0 + q, 32); hz_n[q] = ld_stream(st_z2, p, ch0 + q, 32); }
                 ep.wait_acc();
-#pragma unroll 1
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint4 hs_c[4], hz_c[4];
+                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+                    uint4 hs_c[2], hz_c[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { hs_c[q] = hs_n[q]; hz_c[q] = hz_n[q]; }
-                    if (c0 + 32 < 256) {
+                    for (int q = 0; q < 2; ++q) { hs_c[q] = hs_n[q]; hz_c[q] = hz_n[q]; }
+                    if (c0 < c_last) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 4 + q, 32);
-                            hz_n[q] = ld_stream(st_z2, p, (c0 >> 3) + 4 + q, 32);
+                        for (int q = 0; q < 2; ++q) {
+                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 2 + q, 32);
+                            hz_n[q] = ld_stream(st_z2, p, (c0 >> 3) + 2 + q, 32);
                         }
                     }
-                    uint32_t v[32];
-                    ep.ld_acc(c0, v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int ch = (c0 >> 3) + q;
                         const uint4 hs = hs_c[q];
                         const uint4 hz = hz_c[q];
@@ -489,8 +506,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                         st_stream(st_zb, p, ch, 32, uz);
                         if (l > 0) ep.st_a(ch, uz);
                     }
-                }
-                if (l == 3) write_skip_cols(ep, [](int) { return 0.f; }, st_zb, p);    // zbar_3 = 0 on the PE columns
+                });
+                if (l == 3 && ep.half == 1) write_skip_cols(ep, [](int) { return 0.f; }, st_zb, p);    // zbar_3 = 0 on the PE columns
                 if (l > 0) ep.signal();
             }
         }
