@@ -145,6 +145,55 @@ RNB_API int rnb_final_merge(const float* z_old, int n_old, const float* z_new, i
 RNB_API int rnb_composite_fwd(const rnb_composite_t* p, void* stream);
 RNB_API int rnb_composite_bwd(const rnb_composite_t* p, void* stream);
 
+/* fp32 [n, cols] row-major -> fp16 stream image (cols % 8 == 0; out: rnb_stream_bytes(n, cols)).  Used by the
+ * stand-alone RenderingNetwork.forward (exp_runner.py:613-615 validate_mesh_texture), whose feature vectors arrive
+ * as an fp32 tensor instead of the stream rnb_sdf_fwd_grad writes. */
+RNB_API int rnb_stream_from_rowmajor(const float* x, int64_t n, int cols, void* out, void* stream);
+
+/* ---- NeRF++ background (reference models/fields.py:219-314 NeRF; models/renderer.py:93-130 render_core_outside,
+ *      :255-260 foreground/background blend inside render_core) -- inference only, like its one reference caller
+ *      (render() <- render_novel_image, exp_runner.py:541) ---------------------------------------------------- */
+RNB_API size_t rnb_nerf_wblob_bytes(void);
+RNB_API size_t rnb_nerf_aux_floats(void);
+/* W, b: HOST arrays of 8 DEVICE pointers (pts_linears.{0..7}: [256,84], [256,256] x4, [256,340], [256,256] x2);
+ * Wf [256,256] feature_linear, Wa [1,256] alpha_linear, Wv [128,283] views_linears.0, Wr [3,128] rgb_linear. */
+RNB_API int rnb_nerf_pack(const float* const* W, const float* const* b, const float* Wf, const float* bf, const float* Wa,
+                  const float* ba, const float* Wv, const float* bv, const float* Wr, const float* br, void* wblob,
+                  float* aux, void* stream);
+/* density [n] (raw alpha_linear output), rgb [n,3] (raw rgb_linear output) = NeRF(pts4, dirs).
+ * Either explicit inputs pts4 [n,4] + dirs [n,3] (NeRF.forward), or ray samples: pts->rays_o/rays_d/z with
+ * point = o + d*z, pts4 = [p/r, 1/r], r = max(|p|, 1), dirs = d (render_core_outside, renderer.py:105-113). */
+RNB_API int rnb_nerf_fwd(const rnb_points_t* pts, const float* pts4, const float* dirs, const void* wblob, const float* aux,
+                 float* density, float* rgb, void* stream);
+
+/* render_core with a background model (renderer.py:194-285 with background_alpha / background_sampled_color):
+ * alpha and colour of the 128 SDF samples are blended with the NeRF++ samples by inside_sphere, the n_outside
+ * background samples are appended, then weights / colour are composited over 128 + n_outside samples. */
+typedef struct {
+    int32_t n_rays;
+    const float* rays_o;
+    const float* rays_d;
+    const float* z;             /* [B,128] depths of the SDF pass */
+    const float* sdf;           /* [B*128] at the section mid-points */
+    const float* grad;          /* [B*128,3] */
+    const float* color_in;      /* [B*128,3] colour-network output */
+    const float* variance;      /* device scalar */
+    float cos_anneal_ratio;
+    float sample_dist;
+    const float* z_feed;        /* [B,128+n_outside] sorted depths of the background pass */
+    const float* bg_density;    /* [B*(128+n_outside)] raw NeRF density at the z_feed section mid-points */
+    const float* bg_rgb;        /* [B*(128+n_outside),3] raw NeRF rgb */
+    int32_t n_outside;          /* 1..64 */
+    float* color;               /* out [B,3] */
+    float* weights;             /* out [B,128+n_outside] */
+    float* cdf;                 /* out [B,128] */
+    float* inside;              /* out [B,128] */
+    float* weight_sum;          /* out [B] */
+    float* weight_max;          /* out [B] */
+    float* eik_part;            /* out [B,2] */
+} rnb_composite_bg_t;
+RNB_API int rnb_composite_bg_fwd(const rnb_composite_bg_t* p, void* stream);
+
 /* ---- albedo network (reference RenderingNetwork mode 'no_view_dir', models/fields.py:131-215) ------------- */
 RNB_API size_t rnb_albedo_wblob_bytes(void);
 RNB_API size_t rnb_albedo_aux_floats(void);

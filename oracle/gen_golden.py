@@ -248,11 +248,29 @@ def gen_background(B=8):
     b = synth.make_batch(B, 3, True, 3)
     g = torch.Generator().manual_seed(14)
     r2 = torch.rand(B, 32, generator=g)
+    cap = {}
+    core, outside = renderer.render_core, renderer.render_core_outside
+
+    def core_hook(rays_o, rays_d, z_vals, *a, **k):
+        cap["z_vals"] = z_vals.detach().clone()
+        return core(rays_o, rays_d, z_vals, *a, **k)
+
+    def outside_hook(rays_o, rays_d, z_vals, *a, **k):
+        cap["z_feed"] = z_vals.detach().clone()
+        ret = outside(rays_o, rays_d, z_vals, *a, **k)
+        cap["bg_alpha"], cap["bg_color"] = ret["alpha"].detach().clone(), ret["sampled_color"].detach().clone()
+        return ret
+
+    renderer.render_core, renderer.render_core_outside = core_hook, outside_hook
     with injected_rand([b["t_rand"] + 0.5, r2]):
         out = renderer.render(b["rays_o"], b["rays_d"], b["near"], b["far"], cos_anneal_ratio=1.0,
                               background_rgb=None)
     d = {k: np32(v) for k, v in b.items()}
     d["rand_outside"] = np32(r2)
+    for k, v in cap.items():
+        d[k] = np32(v)
+    for k in ("weight_max", "cdf_fine", "gradients", "s_val"):
+        d["out_" + k] = np32(out[k])
     for k in ("color_fine", "weights", "weight_sum", "inside_sphere", "gradient_error"):
         d["out_" + k] = np32(out[k])
     # direct NeRF pin

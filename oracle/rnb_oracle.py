@@ -686,3 +686,42 @@ def render_core_outside(sd, rays_o, rays_d, z_vals, sample_dist):
     sp = np.where(dens > 20.0, dens, np.log1p(np.exp(np.minimum(dens, 20.0))))
     alpha = 1.0 - np.exp(-sp * dists)
     return alpha, color
+
+
+def render_plain_background(sdf_sd, color_sd, nerf_sd, variance, rays_o, rays_d, z_vals, z_feed,
+                            cos_anneal_ratio=1.0, n_samples=64, background_rgb=None):
+    """render() with n_outside > 0 after the sampling (models/renderer.py:609-648): render_core_outside on
+    z_feed = sort(cat[z_vals, z_vals_outside]), then render_core with background_alpha /
+    background_sampled_color (:255-260): inside_sphere blend of alpha and colour, the outside samples appended."""
+    Ws, bs = sdf_effective(sdf_sd)
+    z = np.asarray(z_vals, F64)
+    B, n = z.shape
+    o = np.asarray(rays_o, F64)
+    d = np.asarray(rays_d, F64)
+    sample_dist = 2.0 / n_samples
+    bg_alpha, bg_color = render_core_outside(nerf_sd, o, d, z_feed, sample_dist)
+    dists = np.concatenate([z[:, 1:] - z[:, :-1], np.full((B, 1), sample_dist)], -1)
+    mid = z + dists * 0.5
+    pts = (o[:, None, :] + d[:, None, :] * mid[:, :, None]).reshape(-1, 3)
+    out, g = sdf_gradient(Ws, bs, pts, keep=True)[:2]
+    sdf = out[:, 0].reshape(B, n)
+    cWs = [weight_norm_fold(color_sd[f"lin{l}.weight_g"], color_sd[f"lin{l}.weight_v"]) for l in range(3)]
+    cbs = [np.asarray(color_sd[f"lin{l}.bias"], F64) for l in range(3)]
+    color = color_forward(cWs, cbs, pts, g, out[:, 1:]).reshape(B, n, 3)
+    inv_s = float(np.clip(np.exp(10.0 * float(variance)), 1e-6, 1e6))
+    ones = np.zeros((1, 1, 1, 3))
+    fw = composite_forward(o, d, z, sdf, g.reshape(B, n, 3), color, ones, inv_s, cos_anneal_ratio, False, n_samples)
+    inside = fw["inside_sphere"]
+    alpha = fw["alpha"] * inside + bg_alpha[:, :n] * (1.0 - inside)
+    alpha = np.concatenate([alpha, bg_alpha[:, n:]], -1)
+    col = color * inside[:, :, None] + bg_color[:, :n] * (1.0 - inside)[:, :, None]
+    col = np.concatenate([col, bg_color[:, n:]], 1)
+    T = np.cumprod(np.concatenate([np.ones((B, 1)), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    w = alpha * T
+    wsum = w.sum(-1, keepdims=True)
+    c = (col * w[:, :, None]).sum(1)
+    if background_rgb is not None:
+        c = c + np.asarray(background_rgb, F64) * (1.0 - wsum)
+    return dict(color_fine=c, weights=w, weight_sum=wsum, weight_max=w.max(-1, keepdims=True),
+                cdf_fine=fw["cdf_fine"], inside_sphere=inside, gradient_error=fw["gradient_error"],
+                gradients=g.reshape(B, n, 3), s_val=fw["s_val"], bg_alpha=bg_alpha, bg_color=bg_color)

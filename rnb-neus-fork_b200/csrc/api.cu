@@ -4,6 +4,7 @@
 #include "dw_params.h"
 #include "render_params.h"
 #include "albedo_params.h"
+#include "nerf_params.h"
 #include <algorithm>
 #include <vector>
 #include <cstring>
@@ -33,6 +34,12 @@ cudaError_t launch_albedo_pack(const float* W0, const float* b0, const float* W1
                                const float* b2, uint8_t* blob, float* aux, cudaStream_t st);
 cudaError_t launch_albedo_fwd(const AlbedoFwdParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_albedo_bwd(const AlbedoBwdParams& P, int sm_count, cudaStream_t st);
+cudaError_t launch_nerf_pack(const float* const* W, const float* const* b, const float* Wf, const float* bf, const float* Wa,
+                             const float* ba, const float* Wv, const float* bv, const float* Wr, const float* br,
+                             uint8_t* blob, float* aux, cudaStream_t st);
+cudaError_t launch_nerf_fwd(const NerfFwdParams& P, int sm_count, cudaStream_t st);
+cudaError_t launch_composite_bg(const rnb_composite_bg_t& P, cudaStream_t st);
+cudaError_t launch_stream_from_rowmajor(const float* x, int64_t n, int cols, int64_t n_pad, uint8_t* out, cudaStream_t st);
 
 struct AlbedoBwdScratch {
     size_t absmax, dz2, dz1, dz0, dw_part, dwcs_part, cs_part, total;
@@ -88,10 +95,10 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
 // ---- optional per-kernel timing (cudaEvents on the launch stream) and a launch counter ------------------------
 enum ProfTag { T_SDF_PACK, T_SDF_FWD, T_SDF_FWD_GRAD, T_SDF_BWD_DATA, T_DW_GEMM, T_COLSUM, T_REDUCE, T_ABSMAX, T_SUM,
                T_COARSE_Z, T_UPSAMPLE, T_FINAL_MERGE, T_COMPOSITE_FWD, T_COMPOSITE_BWD, T_ALBEDO_PACK, T_ALBEDO_FWD,
-               T_ALBEDO_BWD, T_SAMPLE_PDF, T_COUNT };
+               T_ALBEDO_BWD, T_SAMPLE_PDF, T_NERF_PACK, T_NERF_FWD, T_COMPOSITE_BG, T_COUNT };
 static const char* const kProfNames[T_COUNT] = {
     "sdf_pack", "sdf_fwd", "sdf_fwd_grad", "sdf_bwd_data", "dw_gemm", "colsum", "reduce", "absmax", "sum", "coarse_z",
-    "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf"};
+    "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf", "nerf_pack", "nerf_fwd", "composite_bg"};
 struct ProfRec { int tag; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -328,6 +335,45 @@ int rnb_final_merge(const float* z_old, int n_old, const float* z_new, int n_new
 int rnb_composite_fwd(const rnb_composite_t* p, void* stream) { return (int)profiled(T_COMPOSITE_FWD, (cudaStream_t)stream, [&] { return launch_composite(*p, false, (cudaStream_t)stream); }); }
 int rnb_composite_bwd(const rnb_composite_t* p, void* stream) { return (int)profiled(T_COMPOSITE_BWD, (cudaStream_t)stream, [&] { return launch_composite(*p, true, (cudaStream_t)stream); }); }
 
+
+int rnb_stream_from_rowmajor(const float* x, int64_t n, int cols, void* out, void* stream) {
+    if (cols % 8 != 0 || n < 0) return (int)cudaErrorInvalidValue;
+    return (int)launch_stream_from_rowmajor(x, n, cols, rnb_padded_points(n), (uint8_t*)out, (cudaStream_t)stream);
+}
+size_t rnb_nerf_wblob_bytes(void) { return NRFW_BYTES; }
+size_t rnb_nerf_aux_floats(void) { return NRFX_FLOATS; }
+int rnb_nerf_pack(const float* const* W, const float* const* b, const float* Wf, const float* bf, const float* Wa,
+                  const float* ba, const float* Wv, const float* bv, const float* Wr, const float* br, void* wblob,
+                  float* aux, void* stream) {
+    return (int)profiled(T_NERF_PACK, (cudaStream_t)stream, [&] {
+        return launch_nerf_pack(W, b, Wf, bf, Wa, ba, Wv, bv, Wr, br, (uint8_t*)wblob, aux, (cudaStream_t)stream); });
+}
+int rnb_nerf_fwd(const rnb_points_t* pts, const float* pts4, const float* dirs, const void* wblob, const float* aux,
+                 float* density, float* rgb, void* stream) {
+    NerfFwdParams P{};
+    P.n_pts = pts->n_pts;
+    P.n_tiles = n_tiles(pts->n_pts);
+    P.pts4 = pts4; P.dirs = dirs;
+    P.rays_o = pts->rays_o; P.rays_d = pts->rays_d; P.z = pts->z; P.n_per_ray = pts->n_per_ray;
+    if (!pts4 && !(pts->rays_o && pts->rays_d && pts->z && pts->n_per_ray > 0)) return (int)cudaErrorInvalidValue;
+    if (pts4 && !dirs) return (int)cudaErrorInvalidValue;
+    P.wblob = (const uint8_t*)wblob;
+    P.aux = aux;
+    add_step(P.tab, NRFW_L0, 256, NERF_PE_COLS);
+    for (int l = 1; l <= 4; ++l) add_step(P.tab, NRFW_L1 + (uint32_t)(l - 1) * NRFW_MAT, 256, 256);
+    add_step(P.tab, NRFW_L5H, 256, 256);
+    add_step(P.tab, NRFW_L5E, 256, NERF_PE_COLS, 1);
+    add_step(P.tab, NRFW_L6, 256, 256);
+    add_step(P.tab, NRFW_L6 + NRFW_MAT, 256, 256);
+    add_step(P.tab, NRFW_FEAT, 256, 256);
+    add_step(P.tab, NRFW_VF, 128, 256);
+    add_step(P.tab, NRFW_VE, 128, NERF_PEV_COLS, 1);
+    P.density = density; P.rgb = rgb;
+    return (int)profiled(T_NERF_FWD, (cudaStream_t)stream, [&] { return launch_nerf_fwd(P, sm_count(), (cudaStream_t)stream); });
+}
+int rnb_composite_bg_fwd(const rnb_composite_bg_t* p, void* stream) {
+    return (int)profiled(T_COMPOSITE_BG, (cudaStream_t)stream, [&] { return launch_composite_bg(*p, (cudaStream_t)stream); });
+}
 
 size_t rnb_albedo_wblob_bytes(void) { return ALBW_BYTES; }
 size_t rnb_albedo_aux_floats(void) { return ALBX_FLOATS; }

@@ -72,4 +72,24 @@ cudaError_t launch_sdf_pack(const float* const* W, const float* const* b, uint8_
     return cudaGetLastError();
 }
 
+// fp32 [n, cols] row-major -> fp16 stream image [Npad/64][cols/8][64 rows][16 B]; rows >= n are zero-filled
+__global__ void stream_from_rowmajor_kernel(const float* x, int64_t n, int cols, int64_t n_pad, uint8_t* out) {
+    const int nch = cols / 8;
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte chunk row per thread
+    if (id >= n_pad * nch) return;
+    const int64_t p = id / nch;
+    const int ch = (int)(id % nch);
+    __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(p < n ? x[p * cols + ch * 8 + j] : 0.f);
+    *reinterpret_cast<uint4*>(out + stream_off(p, ch, nch)) = *reinterpret_cast<uint4*>(h);
+}
+
+cudaError_t launch_stream_from_rowmajor(const float* x, int64_t n, int cols, int64_t n_pad, uint8_t* out, cudaStream_t st) {
+    if (n_pad == 0) return cudaSuccess;
+    const int64_t total = n_pad * (cols / 8);
+    stream_from_rowmajor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, n, cols, n_pad, out);
+    return cudaGetLastError();
+}
+
 }  // namespace rnb

@@ -461,6 +461,118 @@ cudaError_t launch_final_merge(const float* z_old, int n_old, const float* z_new
         z_old, n_old, z_new, n_new, n_rays, sample_dist, z_out, mid_out);
     return cudaGetLastError();
 }
+// ------------------------------------------------------------------------------------------------ A15
+// render_core with the NeRF++ background (renderer.py:194-285 with background_alpha / background_sampled_color):
+// forward only.  One warp per ray: the 128 SDF samples 4 per lane as in composite_kernel, then the n_outside
+// appended background samples one per lane (two passes for n_outside > 32), the transmittance carried across.
+__device__ __forceinline__ float bg_alpha_of(float density, float dist) {
+    // alpha = 1 - exp(-softplus(density) * dist)   (renderer.py:118; F.softplus beta = 1, threshold = 20)
+    const float sp = density > 20.f ? density : log1pf(expf(density));
+    return 1.f - expf(-sp * dist);
+}
+
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) composite_bg_kernel(const __grid_constant__ rnb_composite_bg_t P) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * RAYS_PER_BLOCK + warp;
+    if (ray >= P.n_rays) return;
+    constexpr int NS = 128;
+    const int n_tot = NS + P.n_outside;
+    const float inv_s = fminf(fmaxf(expf(__ldg(P.variance) * 10.f), 1e-6f), 1e6f);
+    const float o[3] = {P.rays_o[ray * 3], P.rays_o[ray * 3 + 1], P.rays_o[ray * 3 + 2]};
+    const float d[3] = {P.rays_d[ray * 3], P.rays_d[ray * 3 + 1], P.rays_d[ray * 3 + 2]};
+    const float* zf = P.z_feed + (size_t)ray * n_tot;
+    const float* bd = P.bg_density + (size_t)ray * n_tot;
+    const float* brgb = P.bg_rgb + (size_t)ray * n_tot * 3;
+    float col[3] = {0.f, 0.f, 0.f};
+    float wsum = 0.f, wmax = 0.f, en = 0.f, ed = 0.f;
+    float alpha[4], c[4][3], pcs[4], ins[4];
+    float run = 1.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = lane * 4 + k;
+        const size_t gi = (size_t)ray * NS + i;
+        const float z = P.z[gi];
+        const float dist = i + 1 < NS ? P.z[gi + 1] - z : P.sample_dist;
+        const float mid = z + dist * 0.5f;
+        const float pt[3] = {o[0] + d[0] * mid, o[1] + d[1] * mid, o[2] + d[2] * mid};
+        const float g[3] = {P.grad[gi * 3], P.grad[gi * 3 + 1], P.grad[gi * 3 + 2]};
+        SampleFw f;
+        sample_forward(P.sdf[gi], g, d, pt, dist, inv_s, P.cos_anneal_ratio, f);
+        const float a_bg = bg_alpha_of(bd[i], zf[i + 1] - zf[i]);        // i + 1 <= 128 < n_tot
+        alpha[k] = f.alpha * f.inside + a_bg * (1.f - f.inside);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            c[k][j] = P.color_in[gi * 3 + j] * f.inside + sigmoidf_acc(brgb[i * 3 + j]) * (1.f - f.inside);
+        pcs[k] = f.pc;
+        ins[k] = f.inside;
+        en += f.relax * (f.gn - 1.f) * (f.gn - 1.f);
+        ed += f.relax;
+        run *= 1.f - alpha[k] + 1e-7f;
+    }
+    float carry;
+    {
+        const float incl = warp_scan_mul(run, lane);
+        float T = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) T = 1.f;
+        carry = __shfl_sync(FULL, incl, 31);
+        float w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w[k] = alpha[k] * T;
+            T *= 1.f - alpha[k] + 1e-7f;
+            wsum += w[k];
+            wmax = fmaxf(wmax, w[k]);
+            col[0] += w[k] * c[k][0]; col[1] += w[k] * c[k][1]; col[2] += w[k] * c[k][2];
+        }
+        float* wd = P.weights + (size_t)ray * n_tot + lane * 4;
+        wd[0] = w[0]; wd[1] = w[1]; wd[2] = w[2]; wd[3] = w[3];
+        const size_t base = (size_t)ray * NS + lane * 4;
+        *reinterpret_cast<float4*>(P.cdf + base) = make_float4(pcs[0], pcs[1], pcs[2], pcs[3]);
+        *reinterpret_cast<float4*>(P.inside + base) = make_float4(ins[0], ins[1], ins[2], ins[3]);
+    }
+    for (int j0 = 0; j0 < P.n_outside; j0 += 32) {
+        const int i = NS + j0 + lane;
+        const bool on = i < n_tot;
+        float a = 0.f, cc[3] = {0.f, 0.f, 0.f};
+        if (on) {
+            const float dist = i + 1 < n_tot ? zf[i + 1] - zf[i] : P.sample_dist;
+            a = bg_alpha_of(bd[i], dist);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) cc[j] = sigmoidf_acc(brgb[i * 3 + j]);
+        }
+        const float fac = on ? 1.f - a + 1e-7f : 1.f;
+        const float incl = warp_scan_mul(fac, lane);
+        float T = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) T = 1.f;
+        T *= carry;
+        carry *= __shfl_sync(FULL, incl, 31);
+        const float w = a * T;
+        if (on) {
+            P.weights[(size_t)ray * n_tot + i] = w;
+            wsum += w;
+            wmax = fmaxf(wmax, w);
+            col[0] += w * cc[0]; col[1] += w * cc[1]; col[2] += w * cc[2];
+        }
+    }
+    wsum = warp_sum(wsum); wmax = warp_max(wmax); en = warp_sum(en); ed = warp_sum(ed);
+    col[0] = warp_sum(col[0]); col[1] = warp_sum(col[1]); col[2] = warp_sum(col[2]);
+    if (lane == 0) {
+        P.color[ray * 3] = col[0]; P.color[ray * 3 + 1] = col[1]; P.color[ray * 3 + 2] = col[2];
+        P.weight_sum[ray] = wsum;
+        P.weight_max[ray] = wmax;
+        P.eik_part[ray * 2] = en;
+        P.eik_part[ray * 2 + 1] = ed;
+    }
+}
+
+cudaError_t launch_composite_bg(const rnb_composite_bg_t& P, cudaStream_t st) {
+    if (P.n_rays == 0) return cudaSuccess;
+    if (P.n_outside < 1 || P.n_outside > 64) return cudaErrorInvalidValue;
+    const int grid = (P.n_rays + RAYS_PER_BLOCK - 1) / RAYS_PER_BLOCK;
+    composite_bg_kernel<<<grid, 32 * RAYS_PER_BLOCK, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_composite(const CompositeParams& P, bool bwd, cudaStream_t st) {
     if (P.n_rays == 0) return cudaSuccess;
     const int grid = (P.n_rays + RAYS_PER_BLOCK - 1) / RAYS_PER_BLOCK;

@@ -76,11 +76,53 @@ class NeuSRenderer:
     def _sample(self, rays_o, rays_d, near, far, perturb_overwrite):
         if self.n_outside > 0:
             raise NotImplementedError(
-                "rnb_b200: n_outside > 0 (NeRF++ background) is not built yet; every shipped conf sets n_outside = 0 "
-                "and the reference's own render_rnb* raise a shape error with n_outside > 0 (models/renderer.py:530-535 vs :914)")
+                "rnb_b200: render_rnb* with n_outside > 0 has no reference behaviour to match -- the reference's own "
+                "render_rnb* raise a shape error there (models/renderer.py:530-535 vs :914) and every shipped conf sets "
+                "n_outside = 0.  The NeRF++ background is available through render() (reference :556-648).")
         t_rand = self._jitter(len(rays_o), rays_o.device, perturb_overwrite)
         return _ops.hierarchical_sample(self.sdf_network, rays_o, rays_d, near, far, t_rand, self.n_samples,
                                         self.n_importance, self.up_sample_steps)
+
+    def _outside_z(self, batch_size, far, perturbed, device):
+        """stratified inverse-depth samples of the background (reference :562-585): same RNG call as the reference"""
+        z_out = torch.linspace(1e-3, 1.0 - 1.0 / (self.n_outside + 1.0), self.n_outside, device=device)
+        if perturbed:
+            mids = .5 * (z_out[..., 1:] + z_out[..., :-1])
+            upper = torch.cat([mids, z_out[..., -1:]], -1)
+            lower = torch.cat([z_out[..., :1], mids], -1)
+            t_rand = torch.rand([batch_size, z_out.shape[-1]], device=device)
+            z_out = lower[None, :] + (upper - lower)[None, :] * t_rand
+        return far / torch.flip(z_out, dims=[-1]) + 1.0 / self.n_samples
+
+    def _render_with_background(self, rays_o, rays_d, near, far, perturb_overwrite, background_rgb, cos_anneal_ratio):
+        """render() with the NeRF++ background model (reference :556-648, n_outside > 0).  Forward only: its one
+        reference caller (render_novel_image, exp_runner.py:541-551) detaches the result."""
+        batch_size = len(rays_o)
+        if self.n_samples + self.n_importance != 128 or self.n_importance <= 0:
+            raise RuntimeError("rnb_b200: the compositing kernels are specialised for n_samples + n_importance = 128")
+        perturb = self.perturb if perturb_overwrite < 0 else perturb_overwrite
+        t_rand = self._jitter(batch_size, rays_o.device, perturb_overwrite)          # first RNG call (:572)
+        z_outside = self._outside_z(batch_size, far, perturb > 0, rays_o.device)     # second RNG call (:579)
+        z_vals, mid_z = _ops.hierarchical_sample(self.sdf_network, rays_o, rays_d, near, far, t_rand, self.n_samples,
+                                                 self.n_importance, self.up_sample_steps)
+        out = _ops.render_with_background(self, rays_o, rays_d, z_vals, mid_z, z_outside, cos_anneal_ratio,
+                                          2.0 / self.n_samples)
+        color_fine = out["color"]
+        if background_rgb is not None:
+            color_fine = color_fine + background_rgb * (1.0 - out["weight_sum"])
+        eik = out["eik_part"].sum(0)
+        inv_s = torch.exp(self.deviation_network.variance.detach() * 10.0).clip(1e-6, 1e6)
+        return {
+            'color_fine': color_fine,
+            's_val': (1.0 / inv_s).expand(batch_size, 1),
+            'cdf_fine': out["cdf"],
+            'weight_sum': out["weight_sum"],
+            'weight_max': out["weight_max"],
+            'gradients': out["gradients"],
+            'weights': out["weights"],
+            'gradient_error': eik[0] / (eik[1] + 1e-5),
+            'inside_sphere': out["inside"],
+        }
 
     # ------------------------------------------------------------------ RNb renders
     def _render_rnb(self, warmup, rays_o, rays_d, near, far, lights_dir, perturb_overwrite, background_rgb,
@@ -124,6 +166,9 @@ class NeuSRenderer:
 
     def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0):
         """reference models/renderer.py:556-648: colour = sum_i w_i c_i (+ background_rgb * (1 - sum w))"""
+        if self.n_outside > 0:
+            return self._render_with_background(rays_o, rays_d, near, far, perturb_overwrite, background_rgb,
+                                                cos_anneal_ratio)
         batch_size = len(rays_o)
         z_vals, mid_z = self._sample(rays_o, rays_d, near, far, perturb_overwrite)
         ones = torch.ones(1, 1, 1, 3, device=rays_o.device)

@@ -250,6 +250,87 @@ def composite_bwd(p, d_color, d_weight_sum, d_eik, eik_den, want_albedo):
     return out
 
 
+# ----------------------------------------------------------------------------- NeRF++ background
+NERF_SHAPES = {"pts": [(256, 84)] + [(256, 256)] * 4 + [(256, 340)] + [(256, 256)] * 2,
+               "feature_linear": (256, 256), "alpha_linear": (1, 256), "views_linears.0": (128, 283),
+               "rgb_linear": (3, 128)}
+
+
+class NerfPacked:
+    """Packed fp16 operand images + fp32 side table of one NeRF state (D=8, W=256, skips=[4], multires 10/4)."""
+
+    def __init__(self, nerf_module):
+        lib = L.load()
+        sd = {k: v.detach().float().contiguous() for k, v in nerf_module.state_dict().items()}
+        Ws = [sd[f"pts_linears.{i}.weight"] for i in range(8)] if "pts_linears.7.weight" in sd else []
+        ok = ([tuple(w.shape) for w in Ws] == NERF_SHAPES["pts"]
+              and all(tuple(sd.get(k + ".weight", torch.empty(0)).shape) == NERF_SHAPES[k]
+                      for k in ("feature_linear", "alpha_linear", "views_linears.0", "rgb_linear")))
+        if not ok:
+            raise RuntimeError("rnb_b200: the NeRF++ kernel is specialised for the shipped background field "
+                               "(D=8, W=256, d_in=4, multires=10, multires_view=4, skips=[4], use_viewdirs=True)")
+        dev = Ws[0].device
+        L.require_cuda(Ws[0], "NeRF")
+        bs = [sd[f"pts_linears.{i}.bias"] for i in range(8)]
+        self.wblob = torch.empty(lib.rnb_nerf_wblob_bytes(), dtype=torch.uint8, device=dev)
+        self.aux = torch.empty(lib.rnb_nerf_aux_floats(), dtype=torch.float32, device=dev)
+        wp = (C.c_void_p * 8)(*[L.ptr(t) for t in Ws])
+        bp = (C.c_void_p * 8)(*[L.ptr(t) for t in bs])
+        rest = [sd[k] for k in ("feature_linear.weight", "feature_linear.bias", "alpha_linear.weight", "alpha_linear.bias",
+                                "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias")]
+        L.check(lib.rnb_nerf_pack(wp, bp, *[L.ptr(t) for t in rest], L.ptr(self.wblob), L.ptr(self.aux), L.stream_ptr()),
+                "nerf_pack")
+        self._keep = (Ws, bs, rest)
+
+
+def nerf_fwd(packed: NerfPacked, pts=None, pts4=None, dirs=None):
+    """-> (density [n], rgb [n,3]) raw head outputs; either ray samples `pts` (points_rays) or explicit pts4/dirs"""
+    dev = packed.wblob.device
+    if pts is None:
+        pts4, dirs = _f32(pts4).view(-1, 4), _f32(dirs).view(-1, 3)
+        L.require_cuda(pts4, "NeRF.forward")
+        pts = _points(pts4.shape[0])
+    n = pts.n_pts
+    density = torch.empty(n, dtype=torch.float32, device=dev)
+    rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    L.check(L.load().rnb_nerf_fwd(C.byref(pts), L.ptr(pts4), L.ptr(dirs), L.ptr(packed.wblob), L.ptr(packed.aux),
+                                  L.ptr(density), L.ptr(rgb), L.stream_ptr()), "nerf_fwd")
+    return density, rgb
+
+
+def composite_bg_fwd(rays_o, rays_d, z, sdf, grad, color_in, variance, cos_anneal_ratio, sample_dist, z_feed, bg_density,
+                     bg_rgb):
+    """render_core with background_alpha / background_sampled_color (reference models/renderer.py:194-285), forward"""
+    B, n_tot = z_feed.shape
+    assert z.shape[1] == 128, "the compositing kernels are specialised for 128 SDF samples per ray"
+    dev = z.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = dict(color=torch.empty(B, 3, **f32), weights=torch.empty(B, n_tot, **f32), cdf=torch.empty(B, 128, **f32),
+               inside=torch.empty(B, 128, **f32), weight_sum=torch.empty(B, 1, **f32),
+               weight_max=torch.empty(B, 1, **f32), eik_part=torch.empty(B, 2, **f32))
+    p = L.CompositeBg()
+    p.n_rays = B
+    keep = [_f32(t) for t in (rays_o, rays_d, z, sdf, grad, color_in, variance, z_feed, bg_density, bg_rgb)]
+    (p.rays_o, p.rays_d, p.z, p.sdf, p.grad, p.color_in, p.variance, p.z_feed, p.bg_density,
+     p.bg_rgb) = (L.ptr(t) for t in keep)
+    p.cos_anneal_ratio, p.sample_dist, p.n_outside = float(cos_anneal_ratio), float(sample_dist), n_tot - 128
+    p.color, p.weights, p.cdf, p.inside = (L.ptr(out[k]) for k in ("color", "weights", "cdf", "inside"))
+    p.weight_sum, p.weight_max, p.eik_part = (L.ptr(out[k]) for k in ("weight_sum", "weight_max", "eik_part"))
+    L.check(L.load().rnb_composite_bg_fwd(C.byref(p), L.stream_ptr()), "composite_bg_fwd")
+    return out
+
+
+def stream_from_rowmajor(x, cols):
+    """fp32 [n, cols] row-major -> fp16 stream image [Npad/64][cols/8][64][8] (the layout the chain kernels read)"""
+    x = _f32(x).view(-1, cols)
+    L.require_cuda(x, "stream_from_rowmajor")
+    lib = L.load()
+    n = x.shape[0]
+    buf = torch.empty(lib.rnb_stream_bytes(n, cols), dtype=torch.uint8, device=x.device)
+    L.check(lib.rnb_stream_from_rowmajor(L.ptr(x), n, cols, L.ptr(buf), L.stream_ptr()), "stream_from_rowmajor")
+    return buf
+
+
 def stream_to_rowmajor(buf, n_pts, cols, dtype=torch.float16):
     """Decode a stream image [Npad/64][cols/8][64][8] into [n_pts, cols] (tests / debugging)."""
     t = buf.view(dtype).view(-1, cols // 8, 64, 8).permute(0, 2, 1, 3).reshape(-1, cols)

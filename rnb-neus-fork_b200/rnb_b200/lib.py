@@ -42,6 +42,16 @@ class Composite(C.Structure):
                 ("d_var_part", C.c_void_p)]
 
 
+class CompositeBg(C.Structure):
+    """rnb_composite_bg_t"""
+    _fields_ = [("n_rays", C.c_int32), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("z", C.c_void_p),
+                ("sdf", C.c_void_p), ("grad", C.c_void_p), ("color_in", C.c_void_p), ("variance", C.c_void_p),
+                ("cos_anneal_ratio", C.c_float), ("sample_dist", C.c_float), ("z_feed", C.c_void_p),
+                ("bg_density", C.c_void_p), ("bg_rgb", C.c_void_p), ("n_outside", C.c_int32), ("color", C.c_void_p),
+                ("weights", C.c_void_p), ("cdf", C.c_void_p), ("inside", C.c_void_p), ("weight_sum", C.c_void_p),
+                ("weight_max", C.c_void_p), ("eik_part", C.c_void_p)]
+
+
 _lib = None
 
 _VP = C.c_void_p
@@ -71,6 +81,12 @@ _SIGNATURES = {
     "rnb_final_merge": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
     "rnb_composite_fwd": (C.c_int, [C.POINTER(Composite), _VP]),
     "rnb_composite_bwd": (C.c_int, [C.POINTER(Composite), _VP]),
+    "rnb_nerf_wblob_bytes": (C.c_size_t, []),
+    "rnb_nerf_aux_floats": (C.c_size_t, []),
+    "rnb_nerf_pack": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP)] + [_VP] * 11),
+    "rnb_nerf_fwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 7),
+    "rnb_composite_bg_fwd": (C.c_int, [C.POINTER(CompositeBg), _VP]),
+    "rnb_stream_from_rowmajor": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP]),
     "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 9 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
 }
 

@@ -98,11 +98,71 @@ def sdf_forward(sdf_module, x, want_grad):
 
 
 def albedo_forward(color_module, points, normals, view_dirs, feature_vectors):
-    raise NotImplementedError("rnb_b200: stand-alone RenderingNetwork.forward lands with the albedo kernels")
+    """Stand-alone RenderingNetwork.forward, mode 'no_view_dir' (reference models/fields.py:177-215; called directly by
+    validate_mesh_texture, exp_runner.py:613-615).  Forward only: its reference caller detaches the result."""
+    L.require_cuda(points, "RenderingNetwork.forward")
+    if getattr(color_module, "mode", "no_view_dir") != "no_view_dir":
+        raise RuntimeError("rnb_b200: the albedo kernels implement mode='no_view_dir' (the shipped confs)")
+    from . import albedo as A
+    with torch.no_grad():
+        flat = []
+        for W, b in color_module.effective_weights():
+            flat += [W, b]
+        pts = K.points_explicit(points.reshape(-1, 3))
+
+        class _S:
+            pass
+        st = _S()
+        st.feat = K.stream_from_rowmajor(feature_vectors.reshape(-1, 256), 256)
+        nrm = normals.detach().reshape(-1, 3).float().contiguous()
+        out = A.forward(flat, pts, nrm, st).albedo
+    return out
+
+
+def packed_nerf(nerf_module):
+    """Packed NeRF operands, cached until a parameter changes (version counters)."""
+    params = list(nerf_module.parameters())
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    cache = getattr(nerf_module, "_rnb_packed", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            cache = (key, K.NerfPacked(nerf_module))
+        nerf_module._rnb_packed = cache
+    return cache[1]
 
 
 def nerf_forward(nerf_module, input_pts, input_views):
-    raise NotImplementedError("rnb_b200: the NeRF++ background field is not built yet (all shipped confs set n_outside=0)")
+    """NeRF.forward(input_pts [n,4], input_views [n,3]) -> (alpha [n,1], rgb [n,3]) (reference models/fields.py:281-314).
+    Forward only (the background model is reached only through render() -> render_novel_image upstream)."""
+    L.require_cuda(input_pts, "NeRF.forward")
+    with torch.no_grad():
+        dens, rgb = K.nerf_fwd(packed_nerf(nerf_module), pts4=input_pts.reshape(-1, 4), dirs=input_views.reshape(-1, 3))
+    return dens.view(-1, 1), rgb
+
+
+@torch.no_grad()
+def render_with_background(renderer, rays_o, rays_d, z_vals, mid_z, z_outside, cos_anneal_ratio, sample_dist):
+    """render() with n_outside > 0 (reference models/renderer.py:609-631 + render_core_outside :93-130 + the blend in
+    render_core :255-260), forward only.  -> dict of the compositing kernel's outputs + gradients."""
+    o = rays_o.detach().float().contiguous()
+    d = rays_d.detach().float().contiguous()
+    B = o.shape[0]
+    # SDF pass on the 128 hierarchical samples
+    pk = packed_sdf_nograd(renderer.sdf_network)
+    pts = K.points_rays(o, d, mid_z)
+    sdf, grad, _, streams = K.sdf_fwd_grad(pk, pts)
+    from . import albedo as A
+    col = []
+    for W, b in renderer.color_network.effective_weights():
+        col += [W, b]
+    color_in = A.forward(col, pts, grad, streams).albedo
+    # background pass on sort(cat[z_vals, z_vals_outside]) (renderer.py:610-612); both lists are sorted -> rank merge
+    z_feed, mid_feed = K.final_merge(z_vals, z_outside.float().contiguous(), sample_dist)
+    dens, rgb = K.nerf_fwd(packed_nerf(renderer.nerf), pts=K.points_rays(o, d, mid_feed))
+    var = renderer.deviation_network.variance.detach().float().reshape(1).contiguous()
+    out = K.composite_bg_fwd(o, d, z_vals, sdf, grad, color_in, var, cos_anneal_ratio, sample_dist, z_feed, dens, rgb)
+    out["gradients"] = grad.view(B, FINE_SAMPLES, 3)
+    return out
 
 
 # ------------------------------------------------------------------------------------------ sampling

@@ -1,0 +1,134 @@
+"""NeRF++ background and the stand-alone module calls, on the GPU, against the fixtures written
+by the reference (tests/golden/background.npz, sdf_perturbed.npz).  Tolerance: 1e-3 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from gpu_common import build_nets
+from rnb_b200 import kernels as K
+from rnb_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def make_bg_renderer():
+    from models.renderer import NeuSRenderer
+    nerf, sdf, var, col = build_nets(True, device="cpu")
+    synth.perturb_state_dict_(nerf, 0.02, 7)
+    conf = dict(synth.WMASK_CONF["neus_renderer"], n_outside=32)
+    r = NeuSRenderer(nerf.cuda(), sdf.cuda(), var.cuda(), col.cuda(), **conf)
+    r.color_depth = 3
+    return r
+
+
+class RandQueue:
+    """torch.rand returns the queued tensors in order, as in oracle/gen_golden.injected_rand"""
+
+    def __init__(self, values):
+        self.q, self.orig = list(values), torch.rand
+
+    def __enter__(self):
+        def fake(*a, **k):
+            return self.q.pop(0).to(k.get("device", "cpu"))
+        torch.rand = fake
+
+    def __exit__(self, *a):
+        torch.rand = self.orig
+
+
+def test_nerf_forward_module():
+    g = load_golden("background")
+    r = make_bg_renderer()
+    w = np.array([float(p.detach().double().sum()) for _, p in sorted(r.nerf.named_parameters())])
+    assert np.allclose(w, g["nwsum"], atol=1e-6)
+    alpha, rgb = r.nerf(cu(g["nerf_pts"]), cu(g["nerf_dirs"]))
+    assert tuple(alpha.shape) == g["nerf_alpha"].shape and tuple(rgb.shape) == g["nerf_rgb"].shape
+    assert rel_l2(alpha.cpu().numpy(), g["nerf_alpha"]) < 1e-3
+    assert rel_l2(rgb.cpu().numpy(), g["nerf_rgb"]) < 1e-3
+
+
+def test_nerf_ray_mode_matches_explicit():
+    """pts4 = [p/r, 1/r] built in the kernel == the reference's torch expression fed explicitly"""
+    g = load_golden("background")
+    r = make_bg_renderer()
+    o, d, zf = cu(g["rays_o"]), cu(g["rays_d"]), cu(g["z_feed"])
+    _, mid = K.final_merge(zf, None, 2.0 / 64)
+    pk = ops.packed_nerf(r.nerf)
+    dens, rgb = K.nerf_fwd(pk, pts=K.points_rays(o, d, mid))
+    pts = o[:, None, :] + d[:, None, :] * mid[:, :, None]
+    dis = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).clip(1.0, 1e10)
+    pts4 = torch.cat([pts / dis, 1.0 / dis], -1).reshape(-1, 4)
+    dirs = d[:, None, :].expand(pts.shape).reshape(-1, 3)
+    dens2, rgb2 = K.nerf_fwd(pk, pts4=pts4, dirs=dirs)
+    assert rel_l2(dens.cpu().numpy(), dens2.cpu().numpy()) < 2e-4
+    assert rel_l2(rgb.cpu().numpy(), rgb2.cpu().numpy()) < 2e-4
+    # and against the reference's background pass: alpha = 1 - exp(-softplus(density) dists), colour = sigmoid(rgb)
+    dists = torch.cat([zf[:, 1:] - zf[:, :-1], torch.full_like(zf[:, :1], 2.0 / 64)], -1)
+    alpha = 1.0 - torch.exp(-torch.nn.functional.softplus(dens.view(zf.shape)) * dists)
+    assert rel_l2(alpha.cpu().numpy(), g["bg_alpha"]) < 1e-3
+    assert rel_l2(torch.sigmoid(rgb).view(zf.shape[0], -1, 3).cpu().numpy(), g["bg_color"]) < 1e-3
+
+
+def test_render_with_background_identical_samples():
+    g = load_golden("background")
+    r = make_bg_renderer()
+    z_vals = cu(g["z_vals"])
+    _, mid = K.final_merge(z_vals, None, 2.0 / 64)
+    out = ops.render_with_background(r, cu(g["rays_o"]), cu(g["rays_d"]), z_vals, mid, cu(g["z_feed"][:, 128:]), 1.0, 2.0 / 64)
+    eik = out["eik_part"].sum(0)
+    for mine, key in (("color", "color_fine"), ("weight_sum", "weight_sum"), ("weight_max", "weight_max"),
+                      ("cdf", "cdf_fine"), ("gradients", "gradients")):
+        assert tuple(out[mine].shape) == g["out_" + key].shape, key
+        assert rel_l2(out[mine].cpu().numpy(), g["out_" + key]) < 1e-3, (key, rel_l2(out[mine].cpu().numpy(), g["out_" + key]))
+    assert tuple(out["weights"].shape) == (8, 160)
+    # individual weights move by inv_s/10 x the SDF error; ray sums are checked above
+    assert rel_l2(out["weights"].cpu().numpy(), g["out_weights"]) < 5e-3
+    assert np.array_equal(out["inside"].cpu().numpy(), g["out_inside_sphere"])
+    assert abs(float(eik[0] / (eik[1] + 1e-5)) / float(g["out_gradient_error"]) - 1) < 1e-3
+
+
+def test_render_public_call_with_background():
+    g = load_golden("background")
+    r = make_bg_renderer()
+    with RandQueue([torch.from_numpy(g["t_rand"]) + 0.5, torch.from_numpy(g["rand_outside"])]):
+        out = r.render(cu(g["rays_o"]), cu(g["rays_d"]), cu(g["near"]), cu(g["far"]), cos_anneal_ratio=1.0,
+                       background_rgb=None)
+    # own hierarchical sampling: a slightly different quadrature of the same integrand (see test_gpu_e2e)
+    for k in ("color_fine", "weight_sum", "s_val"):
+        assert tuple(out[k].shape) == g["out_" + k].shape, k
+        assert rel_l2(out[k].cpu().numpy(), g["out_" + k]) < 5e-3, k
+    assert tuple(out["weights"].shape) == (8, 160) and tuple(out["inside_sphere"].shape) == (8, 128)
+    assert abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1) < 2e-2
+    # white background term (reference :266-267)
+    with RandQueue([torch.from_numpy(g["t_rand"]) + 0.5, torch.from_numpy(g["rand_outside"])]):
+        out_w = r.render(cu(g["rays_o"]), cu(g["rays_d"]), cu(g["near"]), cu(g["far"]), cos_anneal_ratio=1.0,
+                         background_rgb=torch.ones(1, 3, device="cuda"))
+    expect = out["color_fine"] + (1.0 - out["weight_sum"])
+    assert torch.allclose(out_w["color_fine"], expect, atol=1e-6)
+
+
+def test_render_rnb_with_outside_raises_like_reference():
+    r = make_bg_renderer()
+    g = load_golden("background")
+    with pytest.raises(NotImplementedError):
+        r.render_rnb_warmup(cu(g["rays_o"]), cu(g["rays_d"]), cu(g["near"]), cu(g["far"]), cu(g["lights_dir"]))
+
+
+def test_rendering_network_standalone():
+    """color_network(points, normals, view_dirs, features) as validate_mesh_texture calls it (exp_runner.py:613-615)"""
+    g = load_golden("sdf_perturbed")
+    _, sdf, _, col = build_nets(True)
+    x, nrm, feat = cu(g["x"]), cu(g["grad"]), cu(g["out"][:, 1:])
+    alb = col(x, nrm, nrm, feat)
+    assert tuple(alb.shape) == g["albedo"].shape
+    assert rel_l2(alb.cpu().numpy(), g["albedo"]) < 1e-3
+    # and chained from this repo's own SDF module calls
+    full = sdf(x)
+    grad = sdf.gradient(x).squeeze()
+    alb2 = col(x, grad, grad, full[:, 1:])
+    assert rel_l2(alb2.detach().cpu().numpy(), g["albedo"]) < 1e-3

@@ -179,3 +179,22 @@ def test_background_nerf():
     a, rgb = O.nerf_forward(sd, g["nerf_pts"], g["nerf_dirs"])
     assert rel_l2(a, g["nerf_alpha"]) < 1e-4
     assert rel_l2(rgb, g["nerf_rgb"]) < 1e-4
+
+
+def test_background_render():
+    """render() with the NeRF++ background (n_outside=32) on the reference's own sample depths"""
+    g = load_golden("background")
+    sdf_sd, col_sd, variance, nerf, _ = ref_like_state_dicts(True)
+    synth.perturb_state_dict_(nerf, 0.02, 7)
+    nsd = {k: v.detach().double().numpy() for k, v in nerf.state_dict().items()}
+    r = O.render_plain_background(sdf_sd, col_sd, nsd, variance, g["rays_o"], g["rays_d"], g["z_vals"], g["z_feed"], 1.0)
+    assert rel_l2(r["bg_alpha"], g["bg_alpha"]) < 1e-4
+    assert rel_l2(r["bg_color"], g["bg_color"]) < 1e-5
+    for k in ("color_fine", "weights", "weight_sum", "weight_max", "cdf_fine", "gradients", "s_val"):
+        assert r[k].shape == g["out_" + k].shape, k
+        assert rel_l2(r[k], g["out_" + k]) < 2e-4, (k, rel_l2(r[k], g["out_" + k]))
+    assert np.array_equal(r["inside_sphere"], g["out_inside_sphere"])
+    assert abs(r["gradient_error"] / float(g["out_gradient_error"]) - 1) < 1e-4
+    # the outside samples lie beyond every inside sample: sort(cat) == cat, which the merge kernel relies on only
+    # for speed (it is a general two-list rank merge)
+    assert np.all(np.diff(g["z_feed"], axis=-1) >= 0)
