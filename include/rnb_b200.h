@@ -66,14 +66,15 @@ RNB_API int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const f
 
 /* Double-backward of (sdf, features, gradient) w.r.t. the effective weights (what loss.backward() does to
  * SDFNetwork.forward + .gradient in the reference: exp_runner.py:261 through models/fields.py:82-127).
- * Cotangents: d_sdf [n], d_grad [n,3], d_feat [n,256] fp32 row-major (d_feat may be NULL = zero).
+ * Cotangents: d_sdf [n], d_grad [n,3], and the feature cotangent either as d_feat [n,256] fp32 row-major or as
+ * d_feat16 = the fp16 stream + d_feat16_meta = the device float[2] written by rnb_albedo_bwd (both NULL = zero).
  * st_*: the streams written by rnb_sdf_fwd_grad for the same points.  scratch: rnb_sdf_bwd_scratch_bytes(n).
  * dW, db: HOST arrays of 9 DEVICE pointers, dW[l] fp32 [out_l,in_l] row-major (256x39, 256x256, 256x256,
  * 217x256, 256x256 x4, 257x256), db[l] [out_l]; overwritten. */
 RNB_API size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts);
 RNB_API int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
-                const float* d_feat, const void* st_in0, const void* st_in, const void* st_w,
-                void* scratch, float* const* dW, float* const* db, void* stream);
+                const float* d_feat, const void* d_feat16, const float* d_feat16_meta, const void* st_in0,
+                const void* st_in, const void* st_w, void* scratch, float* const* dW, float* const* db, void* stream);
 
 
 /* ---- per-ray kernels (reference models/renderer.py) ------------------------------------------------------- */
@@ -207,12 +208,16 @@ RNB_API int rnb_albedo_pack(const float* W0, const float* b0, const float* W1, c
 RNB_API int rnb_albedo_fwd(const rnb_points_t* pts, const float* normals, const void* st_feat, const void* wblob, const float* aux,
                    float* albedo, void* st_pe, void* st_h0, void* st_h1, void* stream);
 RNB_API size_t rnb_albedo_bwd_scratch_bytes(int64_t n_pts);
-/* VJP: d_albedo [n,3] -> d_normal [n,3], d_feat [n,256] (fp32 row-major) and the effective-weight gradients
- * dW0 [256,310], db0 [256], dW1 [256,256], db1 [256], dW2 [3,256], db2 [3] (overwritten). */
+/* VJP: d_albedo [n,3] -> d_normal [n,3], the feature cotangent and the effective-weight gradients
+ * dW0 [256,310], db0 [256], dW1 [256,256], db1 [256], dW2 [3,256], db2 [3] (overwritten).
+ * The feature cotangent comes out as d_feat [n,256] fp32 row-major (may be NULL) and/or as d_feat16, an fp16 stream
+ * [Npad x 256] holding d_feat times this call's power-of-two cotangent scale, with d_feat16_meta (device float[2]:
+ * [0] = max |d_albedo| the scale derives from, [1] = max |stored value|); rnb_sdf_bwd consumes the pair directly, which
+ * saves the 1 KB/point fp32 round trip through HBM. */
 RNB_API int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* albedo, const float* d_albedo,
                    const void* st_feat, const void* st_pe, const void* st_h0, const void* st_h1, const void* wblob,
-                   const float* aux, void* scratch, float* d_normal, float* d_feat, float* dW0, float* db0, float* dW1,
-                   float* db1, float* dW2, float* db2, void* stream);
+                   const float* aux, void* scratch, float* d_normal, float* d_feat, void* d_feat16, float* d_feat16_meta,
+                   float* dW0, float* db0, float* dW1, float* db1, float* dW2, float* db2, void* stream);
 
 /* ---- instrumentation -------------------------------------------------------------------------------------- */
 /* total number of kernels this library has launched in this process */

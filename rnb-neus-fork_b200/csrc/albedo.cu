@@ -219,17 +219,41 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
                 });
             }
             ep.signal();
-            // step B0a: d_feat = dz0 W0[:, feat]   -> fp32 [n,256] (input of the SDF backward)
+            // step B0a: d_feat = dz0 W0[:, feat]: fp16 stream in this kernel's cotangent scale (input of the SDF backward,
+            // which rescales by a power of two) + its running max; optionally also fp32 [n,256] (module API / tests)
             ep.wait_acc();
-            ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
-                if (live) {
-                    float4* dst = reinterpret_cast<float4*>(P.d_feat + (size_t)p * 256 + c0);
+            {
+                float m = 0.f;
+                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+                    if (P.st_dfeat16) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]) * inv_scale, __uint_as_float(v[4 * j + 1]) * inv_scale,
-                                             __uint_as_float(v[4 * j + 2]) * inv_scale, __uint_as_float(v[4 * j + 3]) * inv_scale);
+                        for (int q = 0; q < 2; ++q) {
+                            uint4 h;
+                            h.x = pack_h2_sat(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                            h.y = pack_h2_sat(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                            h.z = pack_h2_sat(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                            h.w = pack_h2_sat(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                            st_stream(P.st_dfeat16, p, (c0 >> 3) + q, 32, h);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) m = fmaxf(m, fabsf(__uint_as_float(v[k])));
+                    }
+                    if (P.d_feat && live) {
+                        float4* dst = reinterpret_cast<float4*>(P.d_feat + (size_t)p * 256 + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_float4(__uint_as_float(v[4 * j]) * inv_scale, __uint_as_float(v[4 * j + 1]) * inv_scale,
+                                                 __uint_as_float(v[4 * j + 2]) * inv_scale, __uint_as_float(v[4 * j + 3]) * inv_scale);
+                    }
+                });
+                if (P.st_dfeat16) {
+                    if (!live) m = 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    m = fminf(m, 65504.f);
+                    if (lane == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(P.dfeat_max), __float_as_uint(m));
                 }
-            });
+            }
             ep.signal();       // A (dz0) is reused unchanged by the next GEMM
             // step B0b (N = 64): d_pe = dz0 W0[:, pe] ; d_normal = J_4(normal)^T d_pe[27:54]
             ep.wait_acc();

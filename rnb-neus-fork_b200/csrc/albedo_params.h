@@ -47,7 +47,9 @@ struct AlbedoBwdParams {
     float* dz2;                // out [3][n_pad] fp32 (unscaled)
     uint8_t* st_dz1;           // out fp16 stream (scaled)
     uint8_t* st_dz0;           // out fp16 stream (scaled)
-    float* d_feat;             // out [n,256] fp32
+    float* d_feat;             // out [n,256] fp32 (optional)
+    uint8_t* st_dfeat16;       // out fp16 stream [Npad x 256] = d_feat * cot scale (optional)
+    float* dfeat_max;          // out device scalar: max |stored d_feat| (atomicMax; caller zeroes)
     float* d_normal;           // out [n,3] fp32
 };
 

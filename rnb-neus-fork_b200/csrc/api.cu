@@ -19,8 +19,8 @@ cudaError_t launch_sdf_bwd_data(const SdfBwdParams& P, int sm_count, cudaStream_
 cudaError_t launch_dw_gemm(const DwParams& P, int splits, cudaStream_t st);
 cudaError_t launch_colsum(const ColsumParams& P, int splits, cudaStream_t st);
 cudaError_t launch_reduce(const ReduceParams& P, cudaStream_t st);
-cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out,
-                          cudaStream_t st);
+cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
+                          const float* fold, float* out, cudaStream_t st);
 cudaError_t launch_sum(const float* x, int64_t n, float* out, cudaStream_t st);
 cudaError_t launch_coarse_z(const float* near, const float* far, const float* t_rand, float* z, int n_rays, int n_samples,
                             cudaStream_t st);
@@ -67,7 +67,7 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
 
 // scratch layout of rnb_sdf_bwd
 struct SdfBwdScratch {
-    size_t absmax, uin0, uin, z2, zbar, dfeat, dw_part, dwcs_part, cs_part, total;
+    size_t absmax, uin0, uin, zbar, dfeat, dw_part, dwcs_part, cs_part, total;
     int dw_splits, cs_splits;
 };
 static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
@@ -80,7 +80,6 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     L.absmax = o; o += 256;
     L.uin0 = o; o += s64;
     L.uin = o; o += 8 * s256;
-    L.z2 = o; o += 8 * s256;
     L.zbar = o; o += 8 * s256;
     L.dfeat = o; o += s256;
     o = align_up(o, 256);
@@ -142,11 +141,12 @@ static SdfPointSource to_src(const rnb_points_t* p) {
 }
 
 static void add_step(ChainTable& t, uint32_t off, int n, int k, int accumulate = 0, const void* pf0 = nullptr,
-                     const void* pf1 = nullptr) {
+                     const void* pf1 = nullptr, const void* pf2 = nullptr) {
     t.steps[t.n_steps].accumulate = (uint32_t)accumulate;
-    static const int pf_mode = getenv("RNB_PF") ? atoi(getenv("RNB_PF")) : 3;   // bit0: first stream, bit1: second
+    static const int pf_mode = getenv("RNB_PF") ? atoi(getenv("RNB_PF")) : 7;   // bit0: first stream, bit1: second
     t.steps[t.n_steps].pf[0] = (pf_mode & 1) ? (const uint8_t*)pf0 : nullptr;
     t.steps[t.n_steps].pf[1] = (pf_mode & 2) ? (const uint8_t*)pf1 : nullptr;
+    t.steps[t.n_steps].pf[2] = (pf_mode & 4) ? (const uint8_t*)pf2 : nullptr;
     t.steps[t.n_steps].w_off = off;
     t.steps[t.n_steps].n = (uint16_t)n;
     t.steps[t.n_steps].k = (uint16_t)k;
@@ -211,8 +211,8 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
 size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts) { return sdf_bwd_scratch(n_pts).total; }
 
 int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
-                const float* d_feat, const void* st_in0, const void* st_in, const void* st_w,
-                void* scratch, float* const* dW, float* const* db, void* stream) {
+                const float* d_feat, const void* d_feat16, const float* d_feat16_meta, const void* st_in0,
+                const void* st_in, const void* st_w, void* scratch, float* const* dW, float* const* db, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = pts->n_pts;
     if (n <= 0) return 0;
@@ -220,7 +220,10 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     uint8_t* sc = (uint8_t*)scratch;
     float* absmax = (float*)(sc + L.absmax);
     const size_t SS = rnb_stream_bytes(n, 256);
-    cudaError_t e = profiled(T_ABSMAX, st, [&] { return launch_absmax(d_sdf, n, d_grad, 3 * n, d_feat, d_feat ? 256 * n : 0, absmax, st); });
+    if (d_feat && d_feat16) return (int)cudaErrorInvalidValue;
+    if (d_feat16 && !d_feat16_meta) return (int)cudaErrorInvalidValue;
+    cudaError_t e = profiled(T_ABSMAX, st, [&] {
+        return launch_absmax(d_sdf, n, d_grad, 3 * n, d_feat, d_feat ? 256 * n : 0, d_feat16 ? d_feat16_meta : nullptr, absmax, st); });
     if (e != cudaSuccess) return (int)e;
     // ---- K3a: cotangent streams
     SdfBwdParams P{};
@@ -228,14 +231,31 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     P.n_tiles = n_tiles(n);
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
-    // no L2 prefetch here: measured, this kernel runs at ~65 % of HBM bandwidth and a producer-side prefetch of its
-    // streams raised DRAM reads by 75 % (6.5 ms without, 7.6 ms with, 1 M points)
-    table_forward(P.tab);
-    add_step(P.tab, SDFW_T8, 256, 256);
-    for (int l = 7; l >= 1; --l) add_step(P.tab, sdfw_tr(l), 256, 256);
+    // L2 prefetch of the streams each epilogue reads, both OFF by default: the producer-side bulk prefetch (RNB_BWD_PF)
+    // and per-thread prefetch.global.L2 hints one step ahead (RNB_BWD_TPF) each SLOW this kernel down (6.5 -> 6.7..7.1 ms
+    // at 1 M points, profiles/r01_notes.md): it moves ~25 KB/point through an L2 that is already turning over, and early
+    // fills evict lines that are still waiting to be read.
+    {
+        static const int bwd_pf = getenv("RNB_BWD_PF") ? atoi(getenv("RNB_BWD_PF")) : 0;
+        static const int bwd_tpf = getenv("RNB_BWD_TPF") ? atoi(getenv("RNB_BWD_TPF")) : 0;
+        P.thread_prefetch = bwd_tpf;
+        const uint8_t* a = (const uint8_t*)st_in;
+        const uint8_t* w = (const uint8_t*)st_w;
+        const uint8_t* u = sc + L.uin;
+        // phase A, step l: epilogue reads a_l
+        add_step(P.tab, sdfw_fwd(0), 256, 64, 0, bwd_pf ? a : nullptr);
+        for (int l = 1; l < 8; ++l) add_step(P.tab, sdfw_fwd(l), 256, 256, 0, bwd_pf ? a + (size_t)l * SS : nullptr);
+        // phase B, GEMM yielding abar_l: epilogue reads a_l, w_l, uin_{l+1}
+        add_step(P.tab, SDFW_T8, 256, 256, 0, bwd_pf ? a + (size_t)7 * SS : nullptr, bwd_pf ? w + (size_t)7 * SS : nullptr,
+                 bwd_pf > 1 ? u + (size_t)7 * SS : nullptr);
+        for (int l = 7; l >= 1; --l)
+            add_step(P.tab, sdfw_tr(l), 256, 256, 0, bwd_pf ? a + (size_t)(l - 1) * SS : nullptr,
+                     bwd_pf ? w + (size_t)(l - 1) * SS : nullptr, bwd_pf > 1 ? u + (size_t)(l - 1) * SS : nullptr);
+    }
     P.d_sdf = d_sdf; P.d_grad = d_grad; P.d_feat = d_feat; P.cot_absmax = absmax;
+    P.d_feat16 = (const uint8_t*)d_feat16; P.d_feat16_cot_absmax = d_feat16_meta;
     P.st_in = (const uint8_t*)st_in; P.st_w = (const uint8_t*)st_w;
-    P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_z2 = sc + L.z2; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;
+    P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;
     P.stream_stride = SS;
     e = profiled(T_SDF_BWD_DATA, st, [&] { return launch_sdf_bwd_data(P, sm_count(), st); });
     if (e != cudaSuccess) return (int)e;
@@ -401,16 +421,20 @@ size_t rnb_albedo_bwd_scratch_bytes(int64_t n_pts) { return albedo_bwd_scratch(n
 
 int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* albedo, const float* d_albedo,
                    const void* st_feat, const void* st_pe, const void* st_h0, const void* st_h1, const void* wblob,
-                   const float* aux, void* scratch, float* d_normal, float* d_feat, float* dW0, float* db0, float* dW1,
-                   float* db1, float* dW2, float* db2, void* stream) {
+                   const float* aux, void* scratch, float* d_normal, float* d_feat, void* d_feat16, float* d_feat16_meta,
+                   float* dW0, float* db0, float* dW1, float* db1, float* dW2, float* db2, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = pts->n_pts;
     if (n <= 0) return 0;
     const AlbedoBwdScratch L = albedo_bwd_scratch(n);
     uint8_t* sc = (uint8_t*)scratch;
-    float* absmax = (float*)(sc + L.absmax);
+    // meta[0] = max |d_albedo| (the cotangent scale derives from it), meta[1] = max |stored fp16 d_feat|
+    if (d_feat16 && !d_feat16_meta) return (int)cudaErrorInvalidValue;
+    float* absmax = d_feat16_meta ? d_feat16_meta : (float*)(sc + L.absmax);
     const int64_t n_pad = rnb_padded_points(n);
-    cudaError_t e = profiled(T_ABSMAX, st, [&] { return launch_absmax(d_albedo, 3 * n, nullptr, 0, nullptr, 0, absmax, st); });
+    cudaError_t e = cudaMemsetAsync(absmax, 0, 2 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    e = profiled(T_ABSMAX, st, [&] { return launch_absmax(d_albedo, 3 * n, nullptr, 0, nullptr, 0, nullptr, absmax, st); });
     if (e != cudaSuccess) return (int)e;
     AlbedoBwdParams P{};
     P.src = to_src(pts);
@@ -426,6 +450,7 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     P.dz2 = (float*)(sc + L.dz2);
     P.st_dz1 = sc + L.dz1; P.st_dz0 = sc + L.dz0;
     P.d_feat = d_feat; P.d_normal = d_normal;
+    P.st_dfeat16 = (uint8_t*)d_feat16; P.dfeat_max = absmax + 1;
     e = profiled(T_ALBEDO_BWD, st, [&] { return launch_albedo_bwd(P, sm_count(), st); });
     if (e != cudaSuccess) return (int)e;
     const int n_sub = (int)(n_pad / 64);

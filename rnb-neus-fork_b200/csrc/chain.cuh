@@ -33,7 +33,7 @@ struct ChainStep {
     uint32_t accumulate;   // 1: add onto the accumulator left by the previous step (split-K over two A operands)
     // 256-wide fp16 streams this step's EPILOGUE reads (0 = none): the producer warp pulls the tile's 64 KB of each
     // into L2 one step ahead with cp.async.bulk.prefetch, so the per-row loads of the epilogue are L2 hits
-    const uint8_t* pf[2];
+    const uint8_t* pf[3];
 };
 struct ChainTable {
     int n_steps;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void chain_teardown(const ChainSmem& s, uint32_t tmem
 // warp 0, one lane
 __device__ __forceinline__ void chain_prefetch_step(const ChainTable& tab, int st, int64_t tile) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
         const uint8_t* b = tab.steps[st].pf[k];
         if (b) {
             bulk_prefetch_l2(b + (size_t)tile * 65536, 32768);
@@ -248,6 +248,17 @@ __device__ __forceinline__ void st_stream(uint8_t* base, int64_t p, int chunk, i
 }
 __device__ __forceinline__ uint4 ld_stream(const uint8_t* base, int64_t p, int chunk, int nchunks) {
     return *reinterpret_cast<const uint4*>(base + stream_off(p, chunk, nchunks));
+}
+
+// Pull this thread's part of the NEXT step's stream tile towards L2 a whole step ahead (no registers held, no
+// completion to wait for).  A warp's 32 rows x 16 B of one chunk are 512 contiguous bytes = four 128-byte lines:
+// one lane in eight issues the hint.  The epilogue loads then hit L2 instead of waiting a DRAM round trip per chunk.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_stream_chunks(const uint8_t* base, int64_t p, int chunk0, int n_chunks) {
+    if ((threadIdx.x & 7) == 0) {
+#pragma unroll 4
+        for (int k = 0; k < n_chunks; ++k) prefetch_l2(base + stream_off(p, chunk0 + k, 32));
+    }
 }
 
 // ---- activations (fp32, MUFU based)

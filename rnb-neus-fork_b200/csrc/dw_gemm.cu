@@ -6,6 +6,7 @@
 // Split-K over the points; each CTA keeps a full 256 x N fp32 accumulator in TMEM (2 x 256 columns), dumps one
 // partial, and a small kernel reduces the partials deterministically.  HBM-bound by design (128 FLOP/B).
 #include "common.cuh"
+#include "points.cuh"     // cot_scale_from_max
 #include "dw_params.h"
 
 namespace rnb {
@@ -244,9 +245,12 @@ __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ Red
 }
 
 // ------------------------------------------------------------------ max |x| over up to three fp32 arrays
+// `fold` (optional, device float[2]): a maximum that was taken in another kernel's scaled units -- fold[1] = max of
+// values stored with the power-of-two scale derived from the cotangent absmax fold[0] -- joins the result unscaled.
 __global__ void absmax_kernel(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
-                              float* out) {
+                              const float* fold, float* out) {
     float m = 0.f;
+    if (fold && blockIdx.x == 0 && threadIdx.x == 0) m = fold[1] / cot_scale_from_max(fold[0]);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
@@ -301,11 +305,11 @@ cudaError_t launch_reduce(const ReduceParams& P, cudaStream_t st) {
     reduce_kernel<<<dim3((mx + 255) / 256, P.n_jobs), 256, 0, st>>>(P);
     return cudaGetLastError();
 }
-cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc, float* out,
-                          cudaStream_t st) {
+cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
+                          const float* fold, float* out, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
     if (e != cudaSuccess) return e;
-    absmax_kernel<<<296, 256, 0, st>>>(a, na, b, nb, c, nc, out);
+    absmax_kernel<<<296, 256, 0, st>>>(a, na, b, nb, c, nc, fold, out);
     return cudaGetLastError();
 }
 

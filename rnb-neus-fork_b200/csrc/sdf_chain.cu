@@ -358,6 +358,16 @@ __device__ __noinline__ void emit_skip_ebar(const Epi& ep, const float (&x)[3], 
     write_skip_cols(ep, [&](int i) { return fminf(fmaxf(e[i], -65504.f), 65504.f); }, stream, p);
 }
 
+// zbar = s abar + z2,  z2 = softplus''(z) ua wbar = 100 (1 - s) w (uin / s)   with s = 1 - e, e = exp(-100 a);
+// w = s ua and uin = s wbar are the fp16 streams.  Where s underflows (a -> 0) both streams are (sub)normal-tiny and
+// z2 <= 100 |ua| |uin| is far below the fp16 resolution of any zbar that matters: the quotient is clamped to 0 there.
+__device__ __forceinline__ float zbar_elem(float a, float w, float u, float abar) {
+    const float e = ex2_approx(-144.26950408889634f * a);
+    const float s = 1.f - e;
+    const float r = s > 1e-6f ? rcp_approx(s) : 0.f;
+    return fmaf(s, abar, 100.f * e * w * (u * r));
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __grid_constant__ SdfBwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const ChainSmem s = chain_carve(smem, SDF_A_COLS);
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
         const float* w8row = P.aux + AUX_W8ROW;
         const size_t SS = P.stream_stride;
         const float scale = cot_scale_from_max(__ldg(P.cot_absmax));
+        const float dfeat_rescale = P.d_feat16 ? scale / cot_scale_from_max(__ldg(P.d_feat16_cot_absmax)) : 0.f;
         const int c_last = ep.col0 + EPI_HALF_COLS - 16;
         const int ch0 = ep.col0 >> 3;
         for (int t = 0; t < n_my; ++t) {
@@ -391,116 +402,125 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
             }
             if (ep.half == 0) emit_uin0(ep, x, gb, P.st_uin0, p);
             ep.signal();
-            // ---------------- phase A, l = 0..7:  wbar = W_l uin_l ;  z2_l = 100(1-s)w*wbar ;  ua_bar = s*wbar
+            // ---------------- phase A, l = 0..7:  wbar = W_l uin_l ;  ua_bar_l = s_l * wbar  (-> uin_{l+1})
+            // z2_l = softplus''(z_l) ua_l wbar_l is NOT formed here: phase B recovers it from the uin stream (which the
+            // dW GEMM needs anyway) as z2 = 100 (1 - s) w (uin / s), saving one stream write + one stream read per layer.
 #pragma unroll 1
             for (int l = 0; l < 8; ++l) {
                 const uint8_t* st_s = P.st_in + (size_t)l * SS;      // a_l; s_l = 1 - exp(-100 a_l)
-                const uint8_t* st_w = P.st_w + (size_t)l * SS;
-                uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
                 uint8_t* st_un = P.st_uin + (size_t)l * SS;          // uin_{l+1} = ua_bar_l
-                uint4 hs_n[2], hw_n[2];
+                uint4 hs_n[2];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) { hs_n[q] = ld_stream(st_s, p, ch0 + q, 32); hw_n[q] = ld_stream(st_w, p, ch0 + q, 32); }
+                for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_s, p, ch0 + q, 32);
+                if (P.thread_prefetch) {
+                    // the streams of the NEXT epilogue: a_{l+1}, or (l = 7) w_7 for phase B
+                    if (l < 7) prefetch_stream_chunks(P.st_in + (size_t)(l + 1) * SS, p, ch0, 16);
+                    else prefetch_stream_chunks(P.st_w + (size_t)7 * SS, p, ch0, 16);
+                }
                 ep.wait_acc();
                 ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
-                    uint4 hs_c[2], hw_c[2];
+                    uint4 hs_c[2];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) { hs_c[q] = hs_n[q]; hw_c[q] = hw_n[q]; }
+                    for (int q = 0; q < 2; ++q) hs_c[q] = hs_n[q];
                     if (c0 < c_last) {
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 2 + q, 32);
-                            hw_n[q] = ld_stream(st_w, p, (c0 >> 3) + 2 + q, 32);
-                        }
+                        for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 2 + q, 32);
                     }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int ch = (c0 >> 3) + q;
                         const uint4 hs = hs_c[q];
-                        const uint4 hw = hw_c[q];
-                        const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hwa[4] = {hw.x, hw.y, hw.z, hw.w};
-                        uint32_t z2[4], ub[4];
+                        const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w};
+                        uint32_t ub[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 av = unpack_h2(hsa[j]), wv = unpack_h2(hwa[j]);
-                            // e100 = 100 (1 - s) = 100 exp(-100 a);  s = 1 - e100 / 100
-                            const float e0 = ex2_approx(fmaf(-144.26950408889634f, av.x, 6.643856189774724f));
-                            const float e1 = ex2_approx(fmaf(-144.26950408889634f, av.y, 6.643856189774724f));
+                            const float2 av = unpack_h2(hsa[j]);
                             const float wb0 = __uint_as_float(v[q * 8 + 2 * j]), wb1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
-                            z2[j] = pack_h2_sat(e0 * wv.x * wb0, e1 * wv.y * wb1);
-                            ub[j] = pack_h2_sat(fmaf(-0.01f * e0, wb0, wb0), fmaf(-0.01f * e1, wb1, wb1));
+                            // s wbar = wbar - exp(-100 a) wbar
+                            ub[j] = pack_h2_sat(fmaf(-ex2_approx(-144.26950408889634f * av.x), wb0, wb0),
+                                                fmaf(-ex2_approx(-144.26950408889634f * av.y), wb1, wb1));
                         }
-                        const uint4 uz = make_uint4(z2[0], z2[1], z2[2], z2[3]);
                         const uint4 uu = make_uint4(ub[0], ub[1], ub[2], ub[3]);
-                        st_stream(st_z2, p, ch, 32, uz);
                         st_stream(st_un, p, ch, 32, uu);
                         if (l < 7) ep.st_a(ch, uu);
                     }
                 });
-                if (l == 3 && ep.half == 1) {
-                    emit_skip_ebar(ep, x, gb, st_un, p);
-                    write_skip_cols<false>(ep, [](int) { return 0.f; }, st_z2, p);     // no activation there: z2_3 = 0
-                }
+                if (l == 3 && ep.half == 1) emit_skip_ebar(ep, x, gb, st_un, p);
                 if (l == 7) {
                     // A operand of phase B's first GEMM: d_feat (scaled, fp16); also streamed for dW_8
 #pragma unroll 4
                     for (int k = 0; k < 16; ++k) {
                         const int ch = ch0 + k;
-                        float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
-                        if (live && P.d_feat) {
-                            const float4* src = reinterpret_cast<const float4*>(P.d_feat + (size_t)p * 256 + ch * 8);
-                            f0 = __ldg(src);
-                            f1 = __ldg(src + 1);
+                        uint4 h = make_uint4(0, 0, 0, 0);
+                        if (P.d_feat) {
+                            float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
+                            if (live) {
+                                const float4* src = reinterpret_cast<const float4*>(P.d_feat + (size_t)p * 256 + ch * 8);
+                                f0 = __ldg(src);
+                                f1 = __ldg(src + 1);
+                            }
+                            h.x = pack_h2_sat(f0.x * scale, f0.y * scale); h.y = pack_h2_sat(f0.z * scale, f0.w * scale);
+                            h.z = pack_h2_sat(f1.x * scale, f1.y * scale); h.w = pack_h2_sat(f1.z * scale, f1.w * scale);
+                        } else if (P.d_feat16) {
+                            // fp16 stream written by the albedo backward in ITS cotangent scale: rescale by the
+                            // (power-of-two) ratio of the two scales
+                            const uint4 u = ld_stream(P.d_feat16, p, ch, 32);
+                            const float2 a0 = unpack_h2(u.x), a1 = unpack_h2(u.y), a2 = unpack_h2(u.z), a3 = unpack_h2(u.w);
+                            h.x = pack_h2_sat(a0.x * dfeat_rescale, a0.y * dfeat_rescale);
+                            h.y = pack_h2_sat(a1.x * dfeat_rescale, a1.y * dfeat_rescale);
+                            h.z = pack_h2_sat(a2.x * dfeat_rescale, a2.y * dfeat_rescale);
+                            h.w = pack_h2_sat(a3.x * dfeat_rescale, a3.y * dfeat_rescale);
                         }
-                        uint4 h;
-                        h.x = pack_h2_sat(f0.x * scale, f0.y * scale); h.y = pack_h2_sat(f0.z * scale, f0.w * scale);
-                        h.z = pack_h2_sat(f1.x * scale, f1.y * scale); h.w = pack_h2_sat(f1.z * scale, f1.w * scale);
                         ep.st_a(ch, h);
                         st_stream(P.st_dfeat, p, ch, 32, h);
                     }
                 }
                 ep.signal();
             }
-            // ---------------- phase B: GEMM yields abar_l (l = 7..0);  zbar_l = s_l*abar_l + z2_l
+            // ---------------- phase B: GEMM yields abar_l (l = 7..0);  zbar_l = s_l*abar_l + z2_l,
+            //                  z2_l = softplus''(z_l) ua_l wbar_l = 100 (1 - s_l) w_l uin_{l+1} / s_l
 #pragma unroll 1
             for (int l = 7; l >= 0; --l) {
                 const uint8_t* st_s = P.st_in + (size_t)l * SS;      // a_l
-                const uint8_t* st_z2 = P.st_z2 + (size_t)l * SS;
+                const uint8_t* st_w = P.st_w + (size_t)l * SS;       // w_l = s_l ua_l
+                const uint8_t* st_u = P.st_uin + (size_t)l * SS;     // uin_{l+1} = s_l wbar_l
                 uint8_t* st_zb = P.st_zbar + (size_t)l * SS;
-                uint4 hs_n[2], hz_n[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) { hs_n[q] = ld_stream(st_s, p, ch0 + q, 32); hz_n[q] = ld_stream(st_z2, p, ch0 + q, 32); }
+                // one 16-byte chunk (8 columns) of each stream in flight ahead of the one being consumed
+                uint4 hs_n = ld_stream(st_s, p, ch0, 32), hw_n = ld_stream(st_w, p, ch0, 32), hu_n = ld_stream(st_u, p, ch0, 32);
+                if (P.thread_prefetch) {
+                    if (l > 0) {
+                        prefetch_stream_chunks(P.st_in + (size_t)(l - 1) * SS, p, ch0, 16);
+                        prefetch_stream_chunks(P.st_w + (size_t)(l - 1) * SS, p, ch0, 16);
+                        prefetch_stream_chunks(P.st_uin + (size_t)(l - 1) * SS, p, ch0, 16);
+                    } else if (t + 1 < n_my) {
+                        prefetch_stream_chunks(P.st_in, p + (int64_t)gridDim.x * TILE_M, ch0, 16);    // next tile, phase A l = 0
+                    }
+                }
                 ep.wait_acc();
                 ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
-                    uint4 hs_c[2], hz_c[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) { hs_c[q] = hs_n[q]; hz_c[q] = hz_n[q]; }
-                    if (c0 < c_last) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 2 + q, 32);
-                            hz_n[q] = ld_stream(st_z2, p, (c0 >> 3) + 2 + q, 32);
-                        }
-                    }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int ch = (c0 >> 3) + q;
-                        const uint4 hs = hs_c[q];
-                        const uint4 hz = hz_c[q];
-                        const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
+                        const uint4 hs = hs_n, hw = hw_n, hu = hu_n;
+                        if (ch + 1 < ch0 + 16) {
+                            hs_n = ld_stream(st_s, p, ch + 1, 32);
+                            hw_n = ld_stream(st_w, p, ch + 1, 32);
+                            hu_n = ld_stream(st_u, p, ch + 1, 32);
+                        }
+                        const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hwa[4] = {hw.x, hw.y, hw.z, hw.w},
+                                       hua[4] = {hu.x, hu.y, hu.z, hu.w};
                         float ww[8];
                         if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
                         uint32_t zb[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 av = unpack_h2(hsa[j]), zv = unpack_h2(hza[j]);
-                            const float2 sv = make_float2(sig_from_a(av.x), sig_from_a(av.y));
+                            const float2 av = unpack_h2(hsa[j]), wv = unpack_h2(hwa[j]), uv = unpack_h2(hua[j]);
                             float a0 = __uint_as_float(v[q * 8 + 2 * j]), a1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
                             if (l == 7) {   // abar_7 = d_feat W_8[1:,:] + d_sdf W_8[0,:]
                                 a0 = fmaf(dsdf, ww[2 * j], a0);
                                 a1 = fmaf(dsdf, ww[2 * j + 1], a1);
                             }
-                            zb[j] = pack_h2_sat(fmaf(sv.x, a0, zv.x), fmaf(sv.y, a1, zv.y));
+                            zb[j] = pack_h2_sat(zbar_elem(av.x, wv.x, uv.x, a0), zbar_elem(av.y, wv.y, uv.y, a1));
                         }
                         const uint4 uz = make_uint4(zb[0], zb[1], zb[2], zb[3]);
                         st_stream(st_zb, p, ch, 32, uz);

@@ -57,16 +57,18 @@ struct SdfBwdParams {
     ChainTable tab;
     const float* d_sdf;        // [n_pts]
     const float* d_grad;       // [n_pts,3]
-    const float* d_feat;       // [n_pts,256] fp32 row-major
+    const float* d_feat;       // [n_pts,256] fp32 row-major (or null)
+    const uint8_t* d_feat16;   // alternative: fp16 stream [Npad x 256] scaled by the power of two derived from ...
+    const float* d_feat16_cot_absmax;   // ... this device scalar (the albedo backward's cotangent absmax)
     const float* cot_absmax;   // device scalar: max |cotangent| over the three inputs
     const uint8_t* st_in;      // 8 streams a_l (softplus' is recovered from them)
     const uint8_t* st_w;
     uint8_t* st_uin0;          // fp16 stream [Npad x 64]    uin_0 (scaled)
     uint8_t* st_uin;           // 8 streams, index l = uin_{l+1} = ua_bar_l (scaled)
-    uint8_t* st_z2;            // 8 streams (scratch)
     uint8_t* st_zbar;          // 8 streams, zbar_l (scaled)
     uint8_t* st_dfeat;         // 1 stream, d_feat (scaled)
     size_t stream_stride;
+    int thread_prefetch;       // epilogue threads hint the next step's stream chunks into L2 (prefetch.global.L2)
 };
 
 }  // namespace rnb

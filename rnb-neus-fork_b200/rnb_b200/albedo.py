@@ -46,8 +46,9 @@ def forward(flat, pts, normals, sdf_streams):
     return ctx
 
 
-def backward(ctx, d_albedo):
-    """-> (d_normal [n,3], d_feat [n,256], [dW0, db0, dW1, db1, dW2, db2])"""
+def backward(ctx, d_albedo, want_fp32=False):
+    """-> (d_normal [n,3], d_feat, [dW0, db0, dW1, db1, dW2, db2]); d_feat is (fp16 stream, meta float[2]) for
+    kernels.sdf_bwd(d_feat16=...), or the fp32 [n,256] tensor when want_fp32"""
     lib = L.load()
     dev = ctx.albedo.device
     n = ctx.pts.n_pts
@@ -55,10 +56,13 @@ def backward(ctx, d_albedo):
     scratch = torch.empty(lib.rnb_albedo_bwd_scratch_bytes(n), dtype=torch.uint8, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
     d_normal = torch.empty(n, 3, **f32)
-    d_feat = torch.empty(n, 256, **f32)
+    d_feat = torch.empty(n, 256, **f32) if want_fp32 else None
+    d_feat16 = None if want_fp32 else torch.empty(lib.rnb_stream_bytes(n, 256), dtype=torch.uint8, device=dev)
+    meta = None if want_fp32 else torch.empty(2, **f32)
     grads = [torch.empty(s, **f32) for s in ALBEDO_SHAPES]
     L.check(lib.rnb_albedo_bwd(C.byref(ctx.pts), L.ptr(ctx.normals), L.ptr(ctx.albedo), L.ptr(d_albedo), L.ptr(ctx.feat),
                                L.ptr(ctx.st_pe), L.ptr(ctx.st_h0), L.ptr(ctx.st_h1), L.ptr(ctx.blob), L.ptr(ctx.aux),
-                               L.ptr(scratch), L.ptr(d_normal), L.ptr(d_feat), *[L.ptr(g) for g in grads], L.stream_ptr()),
+                               L.ptr(scratch), L.ptr(d_normal), L.ptr(d_feat), L.ptr(d_feat16), L.ptr(meta),
+                               *[L.ptr(g) for g in grads], L.stream_ptr()),
             "albedo_bwd")
-    return d_normal, d_feat, grads
+    return d_normal, (d_feat if want_fp32 else (d_feat16, meta)), grads

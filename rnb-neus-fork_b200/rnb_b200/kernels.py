@@ -119,8 +119,9 @@ def sdf_fwd_grad(packed: SdfPacked, pts, streams: SdfStreams = None, want_full=F
 SDF_W_SHAPES = [(256, 39), (256, 256), (256, 256), (217, 256), (256, 256), (256, 256), (256, 256), (256, 256), (257, 256)]
 
 
-def sdf_bwd(packed: SdfPacked, pts, streams: SdfStreams, d_sdf, d_grad, d_feat=None, scratch=None):
-    """-> (dWs, dbs): gradients w.r.t. the effective (weight-norm folded) weights and biases."""
+def sdf_bwd(packed: SdfPacked, pts, streams: SdfStreams, d_sdf, d_grad, d_feat=None, scratch=None, d_feat16=None):
+    """-> (dWs, dbs): gradients w.r.t. the effective (weight-norm folded) weights and biases.
+    d_feat: fp32 [n,256], or d_feat16 = (fp16 stream, meta float[2]) as written by the albedo backward."""
     dev = packed.wblob.device
     lib = L.load()
     n = pts.n_pts
@@ -135,8 +136,9 @@ def sdf_bwd(packed: SdfPacked, pts, streams: SdfStreams, d_sdf, d_grad, d_feat=N
     dbs = [torch.empty(s[0], dtype=torch.float32, device=dev) for s in SDF_W_SHAPES]
     wp = (C.c_void_p * N_SDF_LAYERS)(*[L.ptr(t) for t in dWs])
     bp = (C.c_void_p * N_SDF_LAYERS)(*[L.ptr(t) for t in dbs])
+    f16, meta = d_feat16 if d_feat16 is not None else (None, None)
     L.check(lib.rnb_sdf_bwd(C.byref(pts), L.ptr(packed.wblob), L.ptr(packed.aux), L.ptr(d_sdf), L.ptr(d_grad),
-                            L.ptr(d_feat), L.ptr(streams.in0), L.ptr(streams.inl), L.ptr(streams.w),
+                            L.ptr(d_feat), L.ptr(f16), L.ptr(meta), L.ptr(streams.in0), L.ptr(streams.inl), L.ptr(streams.w),
                             L.ptr(scratch), wp, bp, L.stream_ptr()), "sdf_bwd")
     return dWs, dbs, scratch
 

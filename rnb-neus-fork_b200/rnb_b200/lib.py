@@ -71,7 +71,7 @@ _SIGNATURES = {
     "rnb_albedo_pack": (C.c_int, [_VP] * 9),
     "rnb_albedo_fwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 9),
     "rnb_albedo_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
-    "rnb_albedo_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 19),
+    "rnb_albedo_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 21),
     "rnb_launch_count": (C.c_longlong, []),
     "rnb_profile_enable": (None, [C.c_int]),
     "rnb_profile_collect": (C.c_int, [C.c_char_p, C.c_int, _VP, _VP, C.c_int]),
@@ -87,7 +87,7 @@ _SIGNATURES = {
     "rnb_nerf_fwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 7),
     "rnb_composite_bg_fwd": (C.c_int, [C.POINTER(CompositeBg), _VP]),
     "rnb_stream_from_rowmajor": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP]),
-    "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 9 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
+    "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 11 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
 }
 
 

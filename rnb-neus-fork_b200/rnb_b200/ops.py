@@ -245,13 +245,13 @@ class _RnbFine(torch.autograd.Function):
         d_eik = d_eik.detach().float().reshape(1).contiguous()
         bw = K.composite_bwd(cp, d_color, d_wsum, d_eik, ctx.eik_den, ctx.use_albedo)
         d_grad = bw["d_grad"]
-        d_feat = None
+        d_feat16 = None
         col_grads = [None] * ctx.n_col
         if ctx.use_albedo:
             from . import albedo as A
-            d_normal, d_feat, col_grads = A.backward(ctx.actx, bw["d_albedo"])
+            d_normal, d_feat16, col_grads = A.backward(ctx.actx, bw["d_albedo"])
             d_grad = d_grad + d_normal
-        dWs, dbs, _ = K.sdf_bwd(ctx.pk, ctx.pts, ctx.streams, bw["d_sdf"], d_grad, d_feat)
+        dWs, dbs, _ = K.sdf_bwd(ctx.pk, ctx.pts, ctx.streams, bw["d_sdf"], d_grad, None, d_feat16=d_feat16)
         d_var = bw["d_var_part"].sum().reshape(())
         grads = [None, None, None, None, None, None, d_var]
         for W, b in zip(dWs, dbs):

@@ -106,8 +106,18 @@ def test_albedo_fwd_bwd(perturb):
     ref_full = O.color_forward(cWs, cbs, x.cpu().numpy(), grad.cpu().numpy(), full[:, 1:].cpu().numpy())
     assert rel_l2(ctx.albedo.cpu().numpy(), ref_full) < 1e-3
     d_alb = (torch.randn(n, 3, generator=g) * 1e-4 * torch.rand(n, 1, generator=g) ** 3).cuda()
-    d_normal, d_feat, grads = A.backward(ctx, d_alb)
+    d_normal, d_feat, grads = A.backward(ctx, d_alb, want_fp32=True)
     torch.cuda.synchronize()
+    # the training path hands d_feat to the SDF backward as an fp16 stream in the albedo backward's power-of-two
+    # cotangent scale (no fp32 [n,256] round trip): same values, and the recorded maximum is the stream's maximum
+    _, (d_feat16, meta), _ = A.backward(ctx, d_alb)
+    import math
+    mant, expo = math.frexp(float(meta[0]))
+    scale_alb = 2.0 ** (8 - expo)
+    assert abs(float(meta[0]) - float(d_alb.abs().max())) < 1e-12
+    stored = K.stream_to_rowmajor(d_feat16, n, 256).float()
+    assert abs(float(stored.abs().max()) - float(meta[1])) <= 2e-3 * float(meta[1])
+    assert rel_l2((stored / scale_alb).cpu().numpy(), d_feat.cpu().numpy()) < 2e-3
     # (i) backward arithmetic, with the kernel's own ReLU masks (see oracle.color_backward)
     masks = [K.stream_to_rowmajor(ctx.st_h0, n, 256).float().cpu().numpy() > 0,
              K.stream_to_rowmajor(ctx.st_h1, n, 256).float().cpu().numpy() > 0]
