@@ -231,13 +231,13 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     P.n_tiles = n_tiles(n);
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
-    // L2 prefetch of the streams each epilogue reads, both OFF by default: the producer-side bulk prefetch (RNB_BWD_PF)
-    // and per-thread prefetch.global.L2 hints one step ahead (RNB_BWD_TPF) each SLOW this kernel down (6.5 -> 6.7..7.1 ms
-    // at 1 M points, profiles/r01_notes.md): it moves ~25 KB/point through an L2 that is already turning over, and early
-    // fills evict lines that are still waiting to be read.
+    // L2 prefetch of the streams each epilogue reads.  A whole step of lead -- the producer-side bulk prefetch (RNB_BWD_PF)
+    // or per-thread hints issued one step ahead -- SLOWS this kernel down (6.5 -> 6.7..7.1 ms at 1 M points): ~25 KB/point
+    // turn the L2 over so fast that early fills are evicted before they are read.  Hints only RNB_BWD_TPF (= 3) chunks
+    // ahead of the consuming load cover the DRAM latency with a few MB of L2 footprint: 6.5 -> 5.4 ms.
     {
         static const int bwd_pf = getenv("RNB_BWD_PF") ? atoi(getenv("RNB_BWD_PF")) : 0;
-        static const int bwd_tpf = getenv("RNB_BWD_TPF") ? atoi(getenv("RNB_BWD_TPF")) : 0;
+        static const int bwd_tpf = getenv("RNB_BWD_TPF") ? atoi(getenv("RNB_BWD_TPF")) : 3;
         P.thread_prefetch = bwd_tpf;
         const uint8_t* a = (const uint8_t*)st_in;
         const uint8_t* w = (const uint8_t*)st_w;

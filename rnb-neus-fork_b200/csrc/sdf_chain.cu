@@ -412,11 +412,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                 uint4 hs_n[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_s, p, ch0 + q, 32);
-                if (P.thread_prefetch) {
-                    // the streams of the NEXT epilogue: a_{l+1}, or (l = 7) w_7 for phase B
-                    if (l < 7) prefetch_stream_chunks(P.st_in + (size_t)(l + 1) * SS, p, ch0, 16);
-                    else prefetch_stream_chunks(P.st_w + (size_t)7 * SS, p, ch0, 16);
-                }
+                if (P.thread_prefetch) prefetch_stream_chunks(st_s, p, ch0 + 2, P.thread_prefetch);
                 ep.wait_acc();
                 ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
                     uint4 hs_c[2];
@@ -425,6 +421,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                     if (c0 < c_last) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 2 + q, 32);
+                    }
+                    if (P.thread_prefetch && (threadIdx.x & 7) == 0) {
+                        const int pc = (c0 >> 3) + 2 + P.thread_prefetch;        // chunks already covered: up to +1+pf
+                        if (pc + 1 < ch0 + 16) {
+                            prefetch_l2(st_s + stream_off(p, pc, 32));
+                            prefetch_l2(st_s + stream_off(p, pc + 1, 32));
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
@@ -488,13 +491,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                 // one 16-byte chunk (8 columns) of each stream in flight ahead of the one being consumed
                 uint4 hs_n = ld_stream(st_s, p, ch0, 32), hw_n = ld_stream(st_w, p, ch0, 32), hu_n = ld_stream(st_u, p, ch0, 32);
                 if (P.thread_prefetch) {
-                    if (l > 0) {
-                        prefetch_stream_chunks(P.st_in + (size_t)(l - 1) * SS, p, ch0, 16);
-                        prefetch_stream_chunks(P.st_w + (size_t)(l - 1) * SS, p, ch0, 16);
-                        prefetch_stream_chunks(P.st_uin + (size_t)(l - 1) * SS, p, ch0, 16);
-                    } else if (t + 1 < n_my) {
-                        prefetch_stream_chunks(P.st_in, p + (int64_t)gridDim.x * TILE_M, ch0, 16);    // next tile, phase A l = 0
-                    }
+                    prefetch_stream_chunks(st_s, p, ch0 + 1, P.thread_prefetch);
+                    prefetch_stream_chunks(st_w, p, ch0 + 1, P.thread_prefetch);
+                    prefetch_stream_chunks(st_u, p, ch0 + 1, P.thread_prefetch);
                 }
                 ep.wait_acc();
                 ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
@@ -506,6 +505,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                             hs_n = ld_stream(st_s, p, ch + 1, 32);
                             hw_n = ld_stream(st_w, p, ch + 1, 32);
                             hu_n = ld_stream(st_u, p, ch + 1, 32);
+                        }
+                        if (P.thread_prefetch && (threadIdx.x & 7) == 0 && ch + 1 + P.thread_prefetch < ch0 + 16) {
+                            const size_t off = stream_off(p, ch + 1 + P.thread_prefetch, 32);
+                            prefetch_l2(st_s + off);
+                            prefetch_l2(st_w + off);
+                            prefetch_l2(st_u + off);
                         }
                         const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hwa[4] = {hw.x, hw.y, hw.z, hw.w},
                                        hua[4] = {hu.x, hu.y, hu.z, hu.w};
