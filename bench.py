@@ -34,6 +34,19 @@ FLOP_ALB_FWD = 291328
 FLOP_ALB_BWD = 873984 - 291328
 FLOP_PER_RAY = {True: 967303168, False: 855433216}          # with / without the albedo net
 
+# algorithmic HBM bytes per fine point of the stream-carrying kernels (fp16 streams of 512 B/point,
+# 128 B/point for the 64-wide ones; fp32 per-point inputs/outputs).  ncu's dram__bytes for the same launches are in
+# profiles/r01_ncu_summary.md (sdf_fwd_grad 12.1 KB/point, sdf_bwd_data 25.1 KB/point measured).
+BYTES_PER_POINT = {
+    "sdf_fwd_grad": 128 + 8 * 512 + 8 * 512 + 512 + 7 * 512 + 28,           # in0, a_l, w_l, feat written; a_l re-read
+    "sdf_bwd_data": (2 * 8 + 8 + 8) * 512 + 512 + 16 + 128 + (8 + 8 + 1) * 512,  # a(x2), w, uin read; uin0, uin, zbar, dfeat written
+    "dw_gemm": 1280 + 7 * 4 * 512 + 1024,                                     # four operand streams per layer
+    "albedo_fwd": 512 + 128 + 512 + 512 + 36,
+    "albedo_bwd": 2 * 512 + 3 * 512 + 40,
+}
+# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per point of the same launches (profiles/)
+NCU_DRAM_BYTES_PER_POINT = {"sdf_fwd_grad": 12090, "sdf_bwd_data": 25080}
+
 WORKLOADS = {
     "dp8192": dict(rays=8192, no_albedo=False, desc="wmask_rnb.conf train_rnb (render_rnb_warmup fwd + loss + bwd + eikonal), "
                    "8192 rays/GPU, 64+64 samples, 3 lights, albedo net on"),
@@ -324,6 +337,8 @@ def main():
         def full_step(i):
             step(i)
             opt.step()
+        for i in range(2):                          # Adam allocates its state on the first call
+            full_step(i)
         ms_full = timed(full_step, max(3, args.steps // 2))
         units = B * world
         h2d = sum(host_b[0][k].numel() * 4 for k in keys)
@@ -349,15 +364,32 @@ def main():
                 d["tflops"] = FLOP_SDF_ONLY * (B * 112) / (tot / args.steps) / 1e9
             else:
                 d["tflops"] = flops[name] / (tot / cnt) / 1e9
-            d["frac_of_peak"] = d["tflops"] / pk["tf_sustained"]
+            d["frac_of_tensor_peak"] = d["tflops"] / pk["tf_sustained"]
+        if args.workload != "grid512" and name in BYTES_PER_POINT:
+            nbytes = BYTES_PER_POINT[name] * B * 128
+            if name == "dw_gemm":       # two launches per step (SDF net, albedo net): report the SDF one's bytes on the mean
+                nbytes = (BYTES_PER_POINT[name] + (0 if no_albedo else 2816)) * B * 128 / (1 if no_albedo else 2)
+            d["gbs"] = nbytes / (tot / cnt) / 1e6
+            d["frac_of_hbm_peak"] = d["gbs"] / pk["hbm"]
         kernels[name] = d
     cand = [k for k in kernels if "tflops" in kernels[k]]
     top = max(cand, key=lambda k: kernels[k]["share_of_step"]) if cand else None
     roofline = None
     if top:
-        roofline = dict(bound="tensor", kernel=top, achieved=kernels[top]["tflops"], peak=pk["tf_sustained"], unit="TFLOP/s",
-                        frac=kernels[top]["tflops"] / pk["tf_sustained"], traffic=None,
-                        peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})")
+        k = kernels[top]
+        # the roofline that bounds the kernel is the one with the longer floor time
+        hbm_bound = "gbs" in k and k["frac_of_hbm_peak"] > k["frac_of_tensor_peak"]
+        pts_launch = (units_launch if args.workload == "grid512" else B * 128)
+        traffic = NCU_DRAM_BYTES_PER_POINT.get(top)
+        if hbm_bound:
+            roofline = dict(bound="hbm", kernel=top, achieved=k["gbs"], peak=pk["hbm"], unit="GB/s", frac=k["frac_of_hbm_peak"],
+                            traffic=traffic * pts_launch if traffic else None,
+                            peak_source=f"MEASURED_PEAKS.json hbm_gbs ({pk['src']})",
+                            tensor_frac=k["frac_of_tensor_peak"])
+        else:
+            roofline = dict(bound="tensor", kernel=top, achieved=k["tflops"], peak=pk["tf_sustained"], unit="TFLOP/s",
+                            frac=k["frac_of_tensor_peak"], traffic=traffic * pts_launch if traffic else None,
+                            peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})")
     line = dict(metric=metric_name(args.workload), value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate",
                 data="synthetic", config=dict(workload=wl["desc"], weights="geometric init, torch.manual_seed(0)",

@@ -74,13 +74,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
             ep.signal();
             // step 0b: h0 = relu(z0 + b0)
             ep.wait_acc();
-            ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+            ep.sweep_half_bias(b0, [&](int c0, const float (&z)[16]) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    float bb[8], a[8];
-                    load_bias8(b0 + c0 + q * 8, bb);
+                    float a[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bb[j], 0.f);
+                    for (int j = 0; j < 8; ++j) a[j] = fmaxf(z[q * 8 + j], 0.f);
                     uint4 h;
                     h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
                     ep.st_a((c0 >> 3) + q, h);

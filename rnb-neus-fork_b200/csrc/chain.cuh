@@ -235,6 +235,32 @@ struct Epi {
     }
     template <class F>
     __device__ __forceinline__ void sweep_half(F&& f) const { sweep<8>(col0, f); }
+    // sweep_half with a per-column fp32 bias added on the fly: f(c0, z) gets z[k] = acc[c0 + k] + bias[c0 + k].  The
+    // bias loads are software-pipelined one chunk ahead of their use, so their L1 round trip overlaps the previous
+    // chunk's arithmetic instead of stalling the first FADD of every chunk.
+    template <class F>
+    __device__ __forceinline__ void sweep_half_bias(const float* bias, F&& f) const {
+        float4 nb[4];
+        const float4* sp = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nb[k] = __ldg(sp + k);
+        sweep<8>(col0, [&](int c0, const uint32_t (&v)[16]) {
+            float z[16];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                z[4 * k] = __uint_as_float(v[4 * k]) + nb[k].x;
+                z[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + nb[k].y;
+                z[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + nb[k].z;
+                z[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + nb[k].w;
+            }
+            if (c0 + 16 < col0 + EPI_HALF_COLS) {
+                const float4* np = reinterpret_cast<const float4*>(bias + c0 + 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nb[k] = __ldg(np + k);
+            }
+            f(c0, z);
+        });
+    }
 };
 
 // ---- global "stream" images: [n_pts/64 subtiles][C/8 chunks][64 rows][16 B]  (data layout)

@@ -91,16 +91,14 @@ __device__ __noinline__ void nerf_emit_pe_dir(const Epi& ep, const float (&dir)[
 template <bool RELU, bool DOT>
 __device__ __forceinline__ float nerf_layer(const Epi& ep, const float* bias, const float* wdot) {
     float acc = 0.f;
-    ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+    ep.sweep_half_bias(bias, [&](int c0, const float (&z)[16]) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            float bb[8], ww[8], a[8];
-            load_bias8(bias + c0 + q * 8, bb);
+            float ww[8], a[8];
             if (DOT) load_bias8(wdot + c0 + q * 8, ww);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                a[j] = __uint_as_float(v[q * 8 + j]) + bb[j];
-                if (RELU) a[j] = fmaxf(a[j], 0.f);
+                a[j] = RELU ? fmaxf(z[q * 8 + j], 0.f) : z[q * 8 + j];
                 if (DOT) acc = fmaf(a[j], ww[j], acc);
             }
             uint4 h;

@@ -32,26 +32,32 @@ __device__ __forceinline__ void build_in0(const float (&x)[3], const SinCos<6>& 
 // ======================================================================================= K1 / K8
 // One hidden layer's epilogue over this thread's 128 columns: z = acc + b, a = softplus(z) -> next A operand.
 // LAST also reduces this half's part of the sdf row.
-template <bool LAST>
-__device__ __forceinline__ float fwd_layer_plain(const Epi& ep, const float* bias, const float* w8row) {
+__device__ __forceinline__ void fwd_layer_plain(const Epi& ep, const float* bias) {
+    // (the software-pipelined bias sweep of K2 costs this kernel spills: plain loads here)
+    ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float bb[8], a[8];
+            load_bias8(bias + c0 + q * 8, bb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]);
+            uint4 h;
+            h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
+            ep.st_a((c0 >> 3) + q, h);
+        }
+    });
+}
+// last hidden layer: this half's part of sdf = <softplus(z_7), W_8[0,:]>
+__device__ __forceinline__ float fwd_layer_last(const Epi& ep, const float* bias, const float* w8row) {
     float acc = 0.f;
     ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             float bb[8], ww[8];
             load_bias8(bias + c0 + q * 8, bb);
-            if (LAST) load_bias8(w8row + c0 + q * 8, ww);
-            float a[8];
+            load_bias8(w8row + c0 + q * 8, ww);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a[j] = softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]);
-                if (LAST) acc = fmaf(a[j], ww[j], acc);
-            }
-            if (!LAST) {
-                uint4 h;
-                h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
-                ep.st_a((c0 >> 3) + q, h);
-            }
+            for (int j = 0; j < 8; ++j) acc = fmaf(softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]), ww[j], acc);
         }
     });
     return acc;
@@ -131,11 +137,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_kernel(const __grid_
             for (int l = 0; l < 8; ++l) {
                 ep.wait_acc();
                 if (l < 7) {
-                    fwd_layer_plain<false>(ep, bias + l * 256, w8row);
+                    fwd_layer_plain(ep, bias + l * 256);
                     if (l == 3 && ep.half == 1) emit_skip_pe(ep, x, nullptr, p);
                     ep.signal();
                 } else {
-                    part = fwd_layer_plain<true>(ep, bias + l * 256, w8row);
+                    part = fwd_layer_last(ep, bias + l * 256, w8row);
                 }
             }
             // sdf = <a_7, W_8[0,:]> + b_8[0]: the two column halves of a row meet through the (now dead) A buffer
@@ -179,16 +185,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                 ep.wait_acc();
                 uint8_t* st_a_next = P.st_in + (size_t)l * SS;       // in_{l+1} = a_l
                 const float* bl = bias + l * 256;
-                ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
+                ep.sweep_half_bias(bl, [&](int c0, const float (&z)[16]) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        float bb[8], ww[8];
-                        load_bias8(bl + c0 + q * 8, bb);
+                        float ww[8];
                         if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
                         float a[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            a[j] = softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]);
+                            a[j] = softplus100(z[q * 8 + j]);
                             if (l == 7) sdf = fmaf(a[j], ww[j], sdf);
                         }
                         uint4 ha;
