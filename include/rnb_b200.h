@@ -146,6 +146,32 @@ RNB_API int rnb_final_merge(const float* z_old, int n_old, const float* z_new, i
 RNB_API int rnb_composite_fwd(const rnb_composite_t* p, void* stream);
 RNB_API int rnb_composite_bwd(const rnb_composite_t* p, void* stream);
 
+/* ---- ray batches on the device (reference models/dataset.py:351-376 ps_gen_random_rays_at_view_on_all_lights,
+ *      :448-458 near_far_from_sphere, and the light-direction gather of exp_runner.py:214-220).  The reference indexes
+ *      three CPU-resident [views,L,H,W,3] tensors with CPU pixel indices and copies five tensors to the GPU every step;
+ *      here the images stay in HBM and one kernel gathers everything for the given pixels. --------------------------- */
+typedef struct {
+    int32_t n_rays, n_lights, H, W;
+    const float* intrinsics_inv;  /* [4,4] row-major, the view's K^-1 (rows/cols 0..2 used) */
+    const float* pose;            /* [4,4] row-major camera-to-world */
+    const int64_t* pixels_x;      /* [B] */
+    const int64_t* pixels_y;      /* [B] */
+    const float* images;          /* [L,H,W,3] of the view, or NULL */
+    const float* images2;         /* a second image set with the same layout (warm-up / regular), or NULL */
+    const float* mask;            /* [H,W,mask_channels], or NULL */
+    int32_t mask_channels;
+    const float* light_dirs;      /* [L,H,W,3] per-pixel light directions of the view, or NULL */
+    float* rays_o;                /* out [B,3] */
+    float* rays_d;                /* out [B,3] */
+    float* near;                  /* out [B] */
+    float* far;                   /* out [B] */
+    float* mask_out;              /* out [B] or NULL */
+    float* rgb;                   /* out [L,B,3] or NULL */
+    float* rgb2;                  /* out [L,B,3] or NULL */
+    float* lights;                /* out [L,B,3] or NULL */
+} rnb_ray_batch_t;
+RNB_API int rnb_ray_batch(const rnb_ray_batch_t* p, void* stream);
+
 /* fp32 [n, cols] row-major -> fp16 stream image (cols % 8 == 0; out: rnb_stream_bytes(n, cols)).  Used by the
  * stand-alone RenderingNetwork.forward (exp_runner.py:613-615 validate_mesh_texture), whose feature vectors arrive
  * as an fp32 tensor instead of the stream rnb_sdf_fwd_grad writes. */

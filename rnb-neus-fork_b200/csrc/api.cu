@@ -21,7 +21,7 @@ cudaError_t launch_colsum(const ColsumParams& P, int splits, cudaStream_t st);
 cudaError_t launch_reduce(const ReduceParams& P, cudaStream_t st);
 cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
                           const float* fold, float* out, cudaStream_t st);
-cudaError_t launch_sum(const float* x, int64_t n, float* out, cudaStream_t st);
+cudaError_t launch_sum(const float* x, int64_t n, float* partial, float* out, cudaStream_t st);
 cudaError_t launch_coarse_z(const float* near, const float* far, const float* t_rand, float* z, int n_rays, int n_samples,
                             cudaStream_t st);
 cudaError_t launch_upsample(const UpsampleParams& P, cudaStream_t st);
@@ -39,10 +39,11 @@ cudaError_t launch_nerf_pack(const float* const* W, const float* const* b, const
                              uint8_t* blob, float* aux, cudaStream_t st);
 cudaError_t launch_nerf_fwd(const NerfFwdParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_composite_bg(const rnb_composite_bg_t& P, cudaStream_t st);
+cudaError_t launch_ray_batch(const rnb_ray_batch_t& P, cudaStream_t st);
 cudaError_t launch_stream_from_rowmajor(const float* x, int64_t n, int cols, int64_t n_pad, uint8_t* out, cudaStream_t st);
 
 struct AlbedoBwdScratch {
-    size_t absmax, dz2, dz1, dz0, dw_part, dwcs_part, cs_part, total;
+    size_t absmax, sum_part, dz2, dz1, dz0, dw_part, dwcs_part, cs_part, total;
     int dw_splits, cs_splits;
 };
 static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
@@ -54,6 +55,7 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
     L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 32));
     size_t o = 0;
     L.absmax = o; o += 256;
+    L.sum_part = o; o += 3 * 256;
     L.dz2 = o; o += align_up((size_t)3 * n_pad * 4, 256);
     L.dz1 = o; o += s256;
     L.dz0 = o; o += s256;
@@ -67,7 +69,7 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
 
 // scratch layout of rnb_sdf_bwd
 struct SdfBwdScratch {
-    size_t absmax, uin0, uin, zbar, dfeat, dw_part, dwcs_part, cs_part, total;
+    size_t absmax, sum_part, uin0, uin, zbar, dfeat, dw_part, dwcs_part, cs_part, total;
     int dw_splits, cs_splits;
 };
 static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
@@ -78,6 +80,7 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 32));
     size_t o = 0;
     L.absmax = o; o += 256;
+    L.sum_part = o; o += 256;
     L.uin0 = o; o += s64;
     L.uin = o; o += 8 * s256;
     L.zbar = o; o += 8 * s256;
@@ -94,10 +97,10 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
 // ---- optional per-kernel timing (cudaEvents on the launch stream) and a launch counter ------------------------
 enum ProfTag { T_SDF_PACK, T_SDF_FWD, T_SDF_FWD_GRAD, T_SDF_BWD_DATA, T_DW_GEMM, T_COLSUM, T_REDUCE, T_ABSMAX, T_SUM,
                T_COARSE_Z, T_UPSAMPLE, T_FINAL_MERGE, T_COMPOSITE_FWD, T_COMPOSITE_BWD, T_ALBEDO_PACK, T_ALBEDO_FWD,
-               T_ALBEDO_BWD, T_SAMPLE_PDF, T_NERF_PACK, T_NERF_FWD, T_COMPOSITE_BG, T_COUNT };
+               T_ALBEDO_BWD, T_SAMPLE_PDF, T_NERF_PACK, T_NERF_FWD, T_COMPOSITE_BG, T_RAY_BATCH, T_COUNT };
 static const char* const kProfNames[T_COUNT] = {
     "sdf_pack", "sdf_fwd", "sdf_fwd_grad", "sdf_bwd_data", "dw_gemm", "colsum", "reduce", "absmax", "sum", "coarse_z",
-    "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf", "nerf_pack", "nerf_fwd", "composite_bg"};
+    "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf", "nerf_pack", "nerf_fwd", "composite_bg", "ray_batch"};
 struct ProfRec { int tag; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -332,7 +335,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     if (e != cudaSuccess) return (int)e;
     e = profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
     if (e != cudaSuccess) return (int)e;
-    return (int)profiled(T_SUM, st, [&] { return launch_sum(d_sdf, n, db[8], st); });
+    return (int)profiled(T_SUM, st, [&] { return launch_sum(d_sdf, n, (float*)(sc + L.sum_part), db[8], st); });
 }
 
 
@@ -356,6 +359,13 @@ int rnb_composite_fwd(const rnb_composite_t* p, void* stream) { return (int)prof
 int rnb_composite_bwd(const rnb_composite_t* p, void* stream) { return (int)profiled(T_COMPOSITE_BWD, (cudaStream_t)stream, [&] { return launch_composite(*p, true, (cudaStream_t)stream); }); }
 
 
+int rnb_ray_batch(const rnb_ray_batch_t* p, void* stream) {
+    if (!p->intrinsics_inv || !p->pose || !p->pixels_x || !p->pixels_y || !p->rays_o || !p->rays_d || !p->near || !p->far)
+        return (int)cudaErrorInvalidValue;
+    if ((p->rgb && !p->images) || (p->rgb2 && !p->images2) || (p->lights && !p->light_dirs) || (p->mask_out && !p->mask))
+        return (int)cudaErrorInvalidValue;
+    return (int)profiled(T_RAY_BATCH, (cudaStream_t)stream, [&] { return launch_ray_batch(*p, (cudaStream_t)stream); });
+}
 int rnb_stream_from_rowmajor(const float* x, int64_t n, int cols, void* out, void* stream) {
     if (cols % 8 != 0 || n < 0) return (int)cudaErrorInvalidValue;
     return (int)launch_stream_from_rowmajor(x, n, cols, rnb_padded_points(n), (uint8_t*)out, (cudaStream_t)stream);
@@ -502,7 +512,7 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     e = profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
     if (e != cudaSuccess) return (int)e;
     for (int k = 0; k < 3; ++k) {
-        e = profiled(T_SUM, st, [&] { return launch_sum(P.dz2 + (size_t)k * n_pad, n_pad, db2 + k, st); });
+        e = profiled(T_SUM, st, [&] { return launch_sum(P.dz2 + (size_t)k * n_pad, n_pad, (float*)(sc + L.sum_part) + 64 * k, db2 + k, st); });
         if (e != cudaSuccess) return (int)e;
     }
     return 0;

@@ -261,24 +261,37 @@ __global__ void absmax_kernel(const float* a, int64_t na, const float* b, int64_
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
 
-// sum of a small fp32 array (d b_8[0] = sum d_sdf)
-__global__ void __launch_bounds__(1024) sum_kernel(const float* x, int64_t n, float* out) {
-    float v = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) v += x[i];
-    __shared__ float red[32];
+// sum of an fp32 array (d b_8[0] = sum d_sdf; d b_2 of the albedo net): a fixed grid of partial sums in caller scratch
+// (SUM_BLOCKS floats), then one block adds them in a fixed order -- deterministic, no global state.
+constexpr int SUM_BLOCKS = 64;
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
+    v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
     if (threadIdx.x < 32) {
-        v = red[threadIdx.x];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) *out = v;
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     }
+    return v;       // valid in thread 0
 }
-cudaError_t launch_sum(const float* x, int64_t n, float* out, cudaStream_t st) {
-    sum_kernel<<<1, 1024, 0, st>>>(x, n, out);
+__global__ void __launch_bounds__(256) sum_partial_kernel(const float* x, int64_t n, float* partial) {
+    __shared__ float red[8];
+    float v = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)SUM_BLOCKS * 256) v += x[i];
+    v = block_sum_256(v, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(256) sum_final_kernel(const float* partial, float* out) {
+    __shared__ float red[8];
+    const float v = block_sum_256(threadIdx.x < SUM_BLOCKS ? partial[threadIdx.x] : 0.f, red);
+    if (threadIdx.x == 0) *out = v;
+}
+cudaError_t launch_sum(const float* x, int64_t n, float* partial, float* out, cudaStream_t st) {
+    sum_partial_kernel<<<SUM_BLOCKS, 256, 0, st>>>(x, n, partial);
+    sum_final_kernel<<<1, 256, 0, st>>>(partial, out);
     return cudaGetLastError();
 }
 

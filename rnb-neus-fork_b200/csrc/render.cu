@@ -573,6 +573,56 @@ cudaError_t launch_composite_bg(const rnb_composite_bg_t& P, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ ray batches
+// Dataset.ps_gen_random_rays_at_view_on_all_lights + near_far_from_sphere + the per-pixel light gather of train_rnb
+// (reference models/dataset.py:351-376, 448-458; exp_runner.py:214-220) in one launch over device-resident images:
+// one thread per ray.  p = K^-1 [x, y, 1];  v = p / |p|;  d = R v;  o = t;  near/far = -(o.d)/(d.d) -/+ 1.
+__global__ void ray_batch_kernel(const __grid_constant__ rnb_ray_batch_t P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_rays) return;
+    const int x = (int)P.pixels_x[i], y = (int)P.pixels_y[i];
+    const float px = (float)x, py = (float)y;
+    float p[3], v[3], d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        // torch.matmul of a [3,3] with a [3,1]: a plain 3-term dot product per row
+        p[r] = P.intrinsics_inv[r * 4 + 0] * px + P.intrinsics_inv[r * 4 + 1] * py + P.intrinsics_inv[r * 4 + 2];
+    }
+    const float nrm = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) v[r] = p[r] / nrm;
+    float od = 0.f, dd = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        d[r] = P.pose[r * 4 + 0] * v[0] + P.pose[r * 4 + 1] * v[1] + P.pose[r * 4 + 2] * v[2];
+        const float o = P.pose[r * 4 + 3];
+        P.rays_o[i * 3 + r] = o;
+        P.rays_d[i * 3 + r] = d[r];
+        od += o * d[r];
+        dd += d[r] * d[r];
+    }
+    const float mid = 0.5f * (-(2.f * od)) / dd;
+    P.near[i] = mid - 1.f;
+    P.far[i] = mid + 1.f;
+    const size_t pix = (size_t)y * P.W + x;
+    if (P.mask_out) P.mask_out[i] = P.mask[pix * P.mask_channels];
+    const size_t plane = (size_t)P.H * P.W * 3;
+    for (int l = 0; l < P.n_lights; ++l) {
+        const size_t src = (size_t)l * plane + pix * 3, dst = ((size_t)l * P.n_rays + i) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (P.rgb) P.rgb[dst + c] = P.images[src + c];
+            if (P.rgb2) P.rgb2[dst + c] = P.images2[src + c];
+            if (P.lights) P.lights[dst + c] = P.light_dirs[src + c];
+        }
+    }
+}
+cudaError_t launch_ray_batch(const rnb_ray_batch_t& P, cudaStream_t st) {
+    if (P.n_rays == 0) return cudaSuccess;
+    ray_batch_kernel<<<(P.n_rays + 127) / 128, 128, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_composite(const CompositeParams& P, bool bwd, cudaStream_t st) {
     if (P.n_rays == 0) return cudaSuccess;
     const int grid = (P.n_rays + RAYS_PER_BLOCK - 1) / RAYS_PER_BLOCK;

@@ -52,6 +52,16 @@ class CompositeBg(C.Structure):
                 ("weight_max", C.c_void_p), ("eik_part", C.c_void_p)]
 
 
+class RayBatch(C.Structure):
+    """rnb_ray_batch_t"""
+    _fields_ = [("n_rays", C.c_int32), ("n_lights", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("intrinsics_inv", C.c_void_p), ("pose", C.c_void_p), ("pixels_x", C.c_void_p), ("pixels_y", C.c_void_p),
+                ("images", C.c_void_p), ("images2", C.c_void_p), ("mask", C.c_void_p), ("mask_channels", C.c_int32),
+                ("light_dirs", C.c_void_p), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("near", C.c_void_p),
+                ("far", C.c_void_p), ("mask_out", C.c_void_p), ("rgb", C.c_void_p), ("rgb2", C.c_void_p),
+                ("lights", C.c_void_p)]
+
+
 _lib = None
 
 _VP = C.c_void_p
@@ -86,6 +96,7 @@ _SIGNATURES = {
     "rnb_nerf_pack": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP)] + [_VP] * 11),
     "rnb_nerf_fwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 7),
     "rnb_composite_bg_fwd": (C.c_int, [C.POINTER(CompositeBg), _VP]),
+    "rnb_ray_batch": (C.c_int, [C.POINTER(RayBatch), _VP]),
     "rnb_stream_from_rowmajor": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP]),
     "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 11 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
 }

@@ -132,3 +132,45 @@ def test_rendering_network_standalone():
     grad = sdf.gradient(x).squeeze()
     alb2 = col(x, grad, grad, full[:, 1:])
     assert rel_l2(alb2.detach().cpu().numpy(), g["albedo"]) < 1e-3
+
+
+def test_device_ray_batcher_matches_reference_expressions():
+    """rnb_ray_batch vs the torch expressions of Dataset.ps_gen_random_rays_at_view_on_all_lights (dataset.py:351-376),
+    near_far_from_sphere (:448-458) and the light gather of exp_runner.py:214-220"""
+    from rnb_b200.raygen import DeviceRayBatcher
+    g = torch.Generator().manual_seed(3)
+    V, Lh, H, W = 3, 3, 40, 52
+    images = torch.rand(V, Lh, H, W, 3, generator=g)
+    warm = torch.rand(V, Lh, H, W, 3, generator=g)
+    masks = (torch.rand(V, H, W, 3, generator=g) > 0.3).float()
+    lights = torch.nn.functional.normalize(torch.randn(V, Lh, H, W, 3, generator=g), dim=-1)
+    K = torch.eye(4).repeat(V, 1, 1)
+    K[:, 0, 0] = K[:, 1, 1] = 60.0
+    K[:, 0, 2], K[:, 1, 2] = W / 2, H / 2
+    Kinv = torch.inverse(K)
+    pose = torch.eye(4).repeat(V, 1, 1)
+    q, _ = torch.linalg.qr(torch.randn(V, 3, 3, generator=g))
+    pose[:, :3, :3] = q
+    pose[:, :3, 3] = torch.nn.functional.normalize(torch.randn(V, 3, generator=g), dim=-1) * 3.0
+    rb = DeviceRayBatcher(images, warm, masks, lights, Kinv, pose)
+    v, B = 1, 257
+    torch.manual_seed(11)
+    data, w_rgb, rgb, px, py = rb.ps_gen_random_rays_at_view_on_all_lights(v, B)
+    torch.manual_seed(11)
+    pixels_x = torch.randint(low=0, high=W, size=[B])
+    pixels_y = torch.randint(low=0, high=H, size=[B])
+    assert torch.equal(px.cpu(), pixels_x) and torch.equal(py.cpu(), pixels_y)
+    p = torch.stack([pixels_x, pixels_y, torch.ones_like(pixels_y)], dim=-1).float()
+    p = torch.matmul(Kinv[v, None, :3, :3], p[:, :, None]).squeeze()
+    rays_v = p / torch.linalg.norm(p, ord=2, dim=-1, keepdim=True)
+    rays_v = torch.matmul(pose[v, None, :3, :3], rays_v[:, :, None]).squeeze()
+    rays_o = pose[v, None, :3, 3].expand(rays_v.shape)
+    ref = torch.cat([rays_o, rays_v, masks[v][(pixels_y, pixels_x)][:, :1]], dim=-1)
+    assert torch.allclose(data.cpu(), ref, atol=2e-6)
+    assert torch.equal(w_rgb.cpu(), warm[v, :, pixels_y, pixels_x, :]) and torch.equal(rgb.cpu(), images[v, :, pixels_y, pixels_x, :])
+    out = rb.gather(v, pixels_x, pixels_y)
+    a = torch.sum(rays_v ** 2, dim=-1, keepdim=True)
+    b = 2.0 * torch.sum(rays_o * rays_v, dim=-1, keepdim=True)
+    mid = 0.5 * (-b) / a
+    assert torch.allclose(out["near"].cpu(), mid - 1.0, atol=1e-5) and torch.allclose(out["far"].cpu(), mid + 1.0, atol=1e-5)
+    assert torch.equal(out["lights_dir"].cpu(), lights[v, :, pixels_y, pixels_x, :].reshape(Lh, B, 1, 3))
