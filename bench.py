@@ -53,6 +53,8 @@ WORKLOADS = {
     "b512_noalbedo": dict(rays=512, no_albedo=True, desc="wmask_rnb_noalbedo.conf train_rnb --no_albedo, 512 rays, 64+64 samples"),
     "b512": dict(rays=512, no_albedo=False, desc="wmask_rnb.conf train_rnb, 512 rays, 64+64 samples"),
     "grid512": dict(rays=0, no_albedo=True, desc="validate_mesh extract_fields, 512^3 SDF lattice sharded in x-slabs"),
+    "perray": dict(rays=131072, no_albedo=False, desc="compositing + hierarchical-sampling kernels alone at 131072 rays "
+                   "(HBM-bound per-ray kernels, SURVEY 8d algorithmic bytes)"),
 }
 
 
@@ -198,6 +200,69 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def run_perray(args, wl):
+    """The HBM-bound per-ray kernels (K5 compositing fwd/bwd, K6 up-sampling) at a ray count where they stream:
+    achieved GB/s = SURVEY 8d algorithmic bytes / cudaEvent time, against the measured copy bandwidth."""
+    from rnb_b200 import kernels as K
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    pk = peaks()
+    B = wl["rays"]
+    g = torch.Generator(device="cpu").manual_seed(1)
+    o = torch.nn.functional.normalize(torch.randn(1, 3, generator=g), dim=-1).expand(B, 3).contiguous().to(dev) * 3.0
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(B, 3, generator=g).to(dev), dim=-1).contiguous()
+    mid = -(o * d).sum(-1, keepdim=True)
+    near, far = mid - 1.0, mid + 1.0
+    z64 = K.coarse_z(near, far, None, 64)
+    z, _ = K.final_merge(torch.sort(torch.cat([z64, z64 + 0.013], -1), -1)[0].contiguous(), None, 2.0 / 64)
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+    sdf = (pts.norm(dim=-1) - 0.5).reshape(-1).contiguous()
+    grad = torch.nn.functional.normalize(pts, dim=-1).reshape(-1, 3).contiguous()
+    alb = torch.rand(B * 128, 3, device=dev)
+    lights = torch.nn.functional.normalize(torch.randn(3, 1, 1, 3, device=dev), dim=-1)
+    var = torch.full((1,), 0.3, device=dev)
+    cp = K.composite_params(o, d, z, sdf, grad, alb, lights, var, 1.0, 1, 2.0 / 64)
+    d_color = torch.rand(3, B, 3, device=dev) * 1e-4
+    d_ws = torch.rand(B, device=dev) * 1e-4
+    d_eik, eik_den = torch.full((1,), 0.1, device=dev), torch.full((1,), float(B * 100), device=dev)
+    sdf64 = (o[:, None, :] + d[:, None, :] * z64[:, :, None]).norm(dim=-1) - 0.5
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    cases = {
+        # bytes per ray: SURVEY 8d (fp32): read 128*(sdf 4 + grad 12 + albedo 12 + z 4) + o,d 24; write colour/sums 44 + three [128] arrays
+        "composite_fwd": (lambda: K.composite_fwd(cp), 4096 + 24 + 36 + 44 + 3 * 512),
+        "composite_bwd": (lambda: K.composite_bwd(cp, d_color, d_ws, d_eik, eik_den, True), 4096 + 24 + 36 + 40 + 128 * 28 + 4),
+        "upsample": (lambda: K.upsample_step(o, d, z64, sdf64, 64.0, 16), 2 * 256 + 24 + 64),
+        "final_merge": (lambda: K.final_merge(z, None, 2.0 / 64), 512 + 2 * 512),
+    }
+    kernels, tot_bytes, tot_ms = {}, 0.0, 0.0
+    for name, (fn, bpr) in cases.items():
+        ms = timed(fn)
+        kernels[name] = dict(ms_per_launch=ms, bytes_per_ray=bpr, gbs=bpr * B / ms / 1e6, frac_of_hbm_peak=bpr * B / ms / 1e6 / pk["hbm"])
+        if name.startswith("composite"):
+            tot_bytes += bpr * B
+            tot_ms += ms
+    val = tot_bytes / tot_ms / 1e6
+    line = dict(metric="compositing fwd+bwd GB/s", value=val, unit="GB/s", n_gpus=1, steps=20, warmup=3, ms_per_step=tot_ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl["desc"], l2="34 KB/ray x 131072 rays = 4.5 GB of inputs+outputs per pass, far above the 126 MB L2"),
+                roofline=dict(bound="hbm", kernel="composite_fwd+bwd", achieved=val, peak=pk["hbm"], unit="GB/s", frac=val / pk["hbm"],
+                              traffic=None, peak_source=f"MEASURED_PEAKS.json hbm_gbs ({pk['src']})"),
+                kernels=kernels, gpu_launches=23 * len(cases))
+    print(json.dumps(line))
+
+
 def metric_name(workload):
     return "mesh SDF queries/s" if workload == "grid512" else "train rays/s (fwd+bwd+eikonal)"
 
@@ -235,6 +300,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     args.warmup = max(args.warmup, 3)
+    if args.workload == "perray":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_perray(args, wl)
+        return
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
