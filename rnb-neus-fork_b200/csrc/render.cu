@@ -260,7 +260,7 @@ __device__ __forceinline__ void sample_forward(float sdf, const float (&g)[3], c
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) composite_kernel(const __grid_constant__ CompositeParams P) {
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK, 5) composite_kernel(const __grid_constant__ CompositeParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ray = blockIdx.x * RAYS_PER_BLOCK + warp;
     if (ray >= P.n_rays) return;

@@ -1,0 +1,96 @@
+"""Edge cases and size-independent properties of the public path on the GPU (BASELINE.json full sizes included):
+ragged / tiny / empty batches, determinism, exact linearity of the backward in the cotangents, physical bounds of the
+compositing outputs, and a short optimisation run."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_common import build_nets
+from rnb_b200 import synth
+from test_gpu_e2e import loss_fn, make_renderer
+
+pytestmark = pytest.mark.gpu
+
+
+def batch(B, seed=1):
+    return {k: v.cuda() for k, v in synth.make_batch(B, 3, True, seed).items()}
+
+
+def render(renderer, b, **kw):
+    return renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"], cos_anneal_ratio=1.0, **kw)
+
+
+@pytest.mark.parametrize("B", [1, 5, 131])
+def test_tiny_and_ragged_batches(B):
+    """ray counts that fill neither a 4-ray compositing block nor a 128-point MLP tile of the coarse passes"""
+    renderer, sdf, var, col = make_renderer(True)
+    b = batch(B)
+    out = render(renderer, b)
+    assert tuple(out["color_fine"].shape) == (3, B, 3) and tuple(out["weights"].shape) == (B, 128)
+    assert tuple(out["gradients"].shape) == (B, 128, 3) and tuple(out["weight_sum"].shape) == (B, 1)
+    for k in ("color_fine", "weights", "weight_sum", "gradients", "cdf_fine", "gradient_error"):
+        assert torch.isfinite(out[k]).all(), k
+    loss_fn(out, b["true_rgb"], b["mask"], 0.1).backward()
+    for m in (sdf, var, col):
+        for n, p in m.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_empty_point_sets():
+    from rnb_b200 import kernels as K, ops
+    _, sdf, _, _ = build_nets(True)
+    out = sdf.sdf(torch.empty(0, 3, device="cuda"))
+    assert tuple(out.shape) == (0, 1)
+    pk = ops.packed_sdf_nograd(sdf)
+    s, g, full, _ = K.sdf_fwd_grad(pk, K.points_explicit(torch.empty(0, 3, device="cuda")), want_full=True)
+    assert s.numel() == 0 and tuple(g.shape) == (0, 3) and tuple(full.shape) == (0, 257)
+
+
+def test_full_size_bounds_determinism_linearity():
+    """BASELINE.json configs[3] size (8192 rays, 1 M fine points)"""
+    renderer, sdf, var, col = make_renderer(True)
+    b = batch(8192)
+    params = [p for m in (sdf, var, col) for p in m.parameters()]
+
+    def run(scale):
+        for p in params:
+            p.grad = None
+        torch.manual_seed(3)
+        out = render(renderer, b)
+        (loss_fn(out, b["true_rgb"], b["mask"], 0.1) * scale).backward()
+        return out, [p.grad.clone() for p in params]
+
+    out, g1 = run(1.0)
+    w = out["weights"]
+    assert (w >= 0).all() and (out["weight_sum"] <= 1.0 + 1e-4).all() and (out["weight_max"] <= out["weight_sum"] + 1e-6).all()
+    assert ((out["cdf_fine"] >= 0) & (out["cdf_fine"] <= 1)).all()
+    assert set(np.unique(out["inside_sphere"].cpu().numpy())) <= {0.0, 1.0}
+    assert torch.allclose(w.sum(-1, keepdim=True), out["weight_sum"], atol=1e-5)
+    assert float(out["gradient_error"]) >= 0
+    # determinism: fixed split-K order and partial sums -> bitwise identical outputs and gradients
+    out2, g2 = run(1.0)
+    assert torch.equal(out["color_fine"], out2["color_fine"]) and torch.equal(out["gradients"], out2["gradients"])
+    for a, c in zip(g1, g2):
+        assert torch.equal(a, c)
+    # linearity: the backward is linear in the cotangents, and its fp16 operands carry a power-of-two scale derived from
+    # max|cotangent| -- scaling the loss by 4 scales every kernel-side gradient by exactly 4
+    _, g4 = run(4.0)
+    for a, c in zip(g1, g4):
+        assert torch.allclose(4.0 * a, c, rtol=1e-5, atol=1e-12)
+
+
+def test_short_optimisation_run_reduces_loss():
+    renderer, sdf, var, col = make_renderer(False)
+    params = [p for m in (sdf, var, col) for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    b = batch(2048, seed=5)
+    losses = []
+    for it in range(12):
+        opt.zero_grad()
+        torch.manual_seed(it)
+        loss = loss_fn(render(renderer, b), b["true_rgb"], b["mask"], 0.1)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert np.isfinite(losses).all()
+    assert losses[-1] < losses[0], losses
