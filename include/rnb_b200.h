@@ -60,7 +60,10 @@ RNB_API int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float*
 /* SDFNetwork.forward + SDFNetwork.gradient fused (reference models/fields.py:82-127; call site
  * models/renderer.py:492-498).  Writes sdf [n], grad [n,3], the feature stream (fp16 [Npad x 256]) and the
  * activation streams the backward needs: st_in0 [Npad x 64] (layer-0 input), st_in = 8 streams a_l [Npad x 256],
- * st_w = 8 streams w_l = softplus'(z_l) * (dx-chain cotangent).  out_full (optional, may be NULL): fp32 [n,257] like the reference. */
+ * st_w = 8 streams w_l = softplus'(z_l) * (dx-chain cotangent).  out_full (optional, may be NULL): fp32 [n,257] like the reference.
+ * Inference (no backward to follow, e.g. validate_image / render_novel_image): st_w and st_in0 may be NULL -- they are
+ * only read by rnb_sdf_bwd -- which saves 4.1 of the 8.8 KB/point this kernel writes; st_in is still needed (the
+ * kernel's own dx-chain reads it back) and st_feat feeds rnb_albedo_fwd. */
 RNB_API int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* aux, float* out_sdf, float* out_grad,
                      float* out_full, void* st_feat, void* st_in0, void* st_in, void* st_w, void* stream);
 

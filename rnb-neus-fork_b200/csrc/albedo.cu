@@ -35,7 +35,7 @@ __device__ __noinline__ void emit_pe64(const Epi& ep, const float (&x)[3], const
     for (int c = 0; c < 8; ++c) {
         const uint4 u = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
         ep.st_a(c, u);
-        st_stream(stream, p, c, 8, u);
+        if (stream) st_stream(stream, p, c, 8, u);
     }
 }
 
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
                     uint4 h;
                     h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
                     ep.st_a((c0 >> 3) + q, h);
-                    st_stream(P.st_h0, p, (c0 >> 3) + q, 32, h);
+                    if (P.st_h0) st_stream(P.st_h0, p, (c0 >> 3) + q, 32, h);
                 }
             });
             ep.signal();
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
                     }
                     uint4 h;
                     h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
-                    st_stream(P.st_h1, p, (c0 >> 3) + q, 32, h);
+                    if (P.st_h1) st_stream(P.st_h1, p, (c0 >> 3) + q, 32, h);
                 }
             });
             // the two column halves of a row combine their partial dot products through the dead A buffer

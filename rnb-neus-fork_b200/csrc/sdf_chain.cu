@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         hw.z = pack_h2(sig_from_a(s2.x) * ww[4], sig_from_a(s2.y) * ww[5]);
                         hw.w = pack_h2(sig_from_a(s3.x) * ww[6], sig_from_a(s3.y) * ww[7]);
                         ep.st_a(ch, hw);
-                        st_stream(st_w7, p, ch, 32, hw);
+                        if (P.st_w) st_stream(st_w7, p, ch, 32, hw);
                     }
                 });
             }
@@ -287,13 +287,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         hw.z = pack_h2(sig_from_a(s2.x) * u[4], sig_from_a(s2.y) * u[5]);
                         hw.w = pack_h2(sig_from_a(s3.x) * u[6], sig_from_a(s3.y) * u[7]);
                         ep.st_a(ch, hw);
-                        st_stream(st_wp, p, ch, 32, hw);
+                        if (P.st_w) st_stream(st_wp, p, ch, 32, hw);
                     }
                 });
                 if (l == 4) {
                     if (ep.half == 1) {
                         // columns 217..255 of layer 4's input are the PE, not activations: w_3 = 0 there
-                        write_skip_cols(ep, [](int) { return 0.f; }, st_wp, p);
+                        write_skip_cols(ep, [](int) { return 0.f; }, P.st_w ? st_wp : nullptr, p);
                     } else {
                         // uin_4[217:] is d sdf / d e through the skip connection: fold it into the gradient now
                         SinCos<6> sc;

@@ -27,8 +27,8 @@ def pack(flat, device):
     return blob, aux, keep
 
 
-def forward(flat, pts, normals, sdf_streams):
-    """-> AlbedoCtx with .albedo [n,3] and the streams kept for the backward."""
+def forward(flat, pts, normals, sdf_streams, for_backward=True):
+    """-> AlbedoCtx with .albedo [n,3] and (for_backward) the streams kept for the backward."""
     lib = L.load()
     dev = normals.device
     n = pts.n_pts
@@ -36,9 +36,9 @@ def forward(flat, pts, normals, sdf_streams):
     ctx.blob, ctx.aux, ctx.keep = pack(flat, dev)
     ctx.pts, ctx.normals, ctx.feat = pts, normals, sdf_streams.feat
     u8 = dict(dtype=torch.uint8, device=dev)
-    ctx.st_pe = torch.empty(lib.rnb_stream_bytes(n, 64), **u8)
-    ctx.st_h0 = torch.empty(lib.rnb_stream_bytes(n, 256), **u8)
-    ctx.st_h1 = torch.empty(lib.rnb_stream_bytes(n, 256), **u8)
+    ctx.st_pe = torch.empty(lib.rnb_stream_bytes(n, 64), **u8) if for_backward else None
+    ctx.st_h0 = torch.empty(lib.rnb_stream_bytes(n, 256), **u8) if for_backward else None
+    ctx.st_h1 = torch.empty(lib.rnb_stream_bytes(n, 256), **u8) if for_backward else None
     ctx.albedo = torch.empty(n, 3, dtype=torch.float32, device=dev)
     L.check(lib.rnb_albedo_fwd(C.byref(pts), L.ptr(normals), L.ptr(ctx.feat), L.ptr(ctx.blob), L.ptr(ctx.aux),
                                L.ptr(ctx.albedo), L.ptr(ctx.st_pe), L.ptr(ctx.st_h0), L.ptr(ctx.st_h1), L.stream_ptr()),

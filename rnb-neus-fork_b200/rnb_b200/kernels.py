@@ -88,7 +88,7 @@ def sdf_fwd(packed: SdfPacked, pts, out=None, out_scale=1.0):
 class SdfStreams:
     """fp16 activation streams written by sdf_fwd_grad and consumed by the backward kernels."""
 
-    def __init__(self, n_pts, device):
+    def __init__(self, n_pts, device, for_backward=True):
         lib = L.load()
         self.n_pts = n_pts
         self.n_pad = lib.rnb_padded_points(n_pts)
@@ -97,16 +97,17 @@ class SdfStreams:
         u8 = dict(dtype=torch.uint8, device=device)
         self.stride = s256
         self.feat = torch.empty(s256, **u8)
-        self.in0 = torch.empty(s64, **u8)
+        # in0 and w are read only by the backward: an inference pass neither allocates nor writes them
+        self.in0 = torch.empty(s64, **u8) if for_backward else None
         self.inl = torch.empty(8 * s256, **u8)
-        self.w = torch.empty(8 * s256, **u8)
+        self.w = torch.empty(8 * s256, **u8) if for_backward else None
 
 
-def sdf_fwd_grad(packed: SdfPacked, pts, streams: SdfStreams = None, want_full=False):
+def sdf_fwd_grad(packed: SdfPacked, pts, streams: SdfStreams = None, want_full=False, for_backward=True):
     dev = packed.wblob.device
     n = pts.n_pts
     if streams is None:
-        streams = SdfStreams(n, dev)
+        streams = SdfStreams(n, dev, for_backward)
     sdf = torch.empty(n, dtype=torch.float32, device=dev)
     grad = torch.empty(n, 3, dtype=torch.float32, device=dev)
     full = torch.empty(n, 257, dtype=torch.float32, device=dev) if want_full else None

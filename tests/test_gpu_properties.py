@@ -94,3 +94,18 @@ def test_short_optimisation_run_reduces_loss():
         losses.append(float(loss))
     assert np.isfinite(losses).all()
     assert losses[-1] < losses[0], losses
+
+
+def test_no_grad_fast_path_matches_training_forward():
+    """validate_image renders under torch.no_grad(): same outputs as the autograd path, without the backward's streams"""
+    renderer, sdf, var, col = make_renderer(True)
+    b = batch(517)
+    for no_albedo in (False, True):
+        torch.manual_seed(5)
+        ref = render(renderer, b, no_albedo=no_albedo)
+        with torch.no_grad():
+            torch.manual_seed(5)
+            out = render(renderer, b, no_albedo=no_albedo)
+        for k in ("color_fine", "weights", "weight_sum", "weight_max", "gradients", "cdf_fine", "inside_sphere", "gradient_error"):
+            assert torch.equal(out[k], ref[k].detach()), k
+            assert not out[k].requires_grad
