@@ -37,6 +37,7 @@ struct ChainStep {
 };
 struct ChainTable {
     int n_steps;
+    int weights_evict_last;   // load the weight slices with an L2 evict-last policy (pays off only under heavy stream traffic)
     ChainStep steps[MAX_STEPS];
 };
 
@@ -106,6 +107,7 @@ __device__ __forceinline__ void chain_prefetch_step(const ChainTable& tab, int s
 
 __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTable& tab, const uint8_t* wblob, int n_my_tiles) {
     uint32_t it = 0;
+    const uint64_t keep = l2_policy_evict_last();
     for (int t = 0; t < n_my_tiles; ++t) {
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
         for (int st = 0; st < tab.n_steps; ++st) {
@@ -120,7 +122,8 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
                 const uint32_t slot = it % RING_STAGES, ph = (it / RING_STAGES) & 1;
                 mbar_wait(&s.empty[slot], ph ^ 1);
                 mbar_expect_tx(&s.full[slot], bytes);
-                bulk_g2s(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot]);
+                if (tab.weights_evict_last) bulk_g2s_hint(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot], keep);
+                else bulk_g2s(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot]);
             }
         }
     }
