@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
             // A <- feature tile (already fp16, chunked)
 #pragma unroll 8
             for (int k = 0; k < 16; ++k) ep.st_a(ch0 + k, ld_stream(P.st_feat, p, ch0 + k, 32));
+            // the next tile's feature rows: hint them into L2 now, three GEMM steps before they are copied
+            if (t + 1 < n_my) prefetch_stream_chunks(P.st_feat, p + (int64_t)gridDim.x * TILE_M, ch0, 16);
             ep.signal();
             // step 0a done (features consumed): A[:, 0:64] <- positional encodings
             ep.wait_acc();
@@ -350,12 +352,10 @@ static inline int chain_grid2(int n_tiles, int sm_count) {
 }
 
 cudaError_t launch_albedo_fwd(const AlbedoFwdParams& P, int sm_count, cudaStream_t st) {
-    static bool attr = false;
     const int smem = chain_smem_bytes(ALB_A_COLS);
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(albedo_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)albedo_fwd_kernel, smem);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (P.n_tiles == 0) return cudaSuccess;
     albedo_fwd_kernel<<<chain_grid2(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
@@ -363,12 +363,10 @@ cudaError_t launch_albedo_fwd(const AlbedoFwdParams& P, int sm_count, cudaStream
 }
 
 cudaError_t launch_albedo_bwd(const AlbedoBwdParams& P, int sm_count, cudaStream_t st) {
-    static bool attr = false;
     const int smem = chain_smem_bytes(ALB_A_COLS);
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(albedo_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)albedo_bwd_kernel, smem);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (P.n_tiles == 0) return cudaSuccess;
     albedo_bwd_kernel<<<chain_grid2(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);

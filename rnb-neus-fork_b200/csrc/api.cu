@@ -125,14 +125,16 @@ static cudaError_t profiled(int tag, cudaStream_t st, F&& f) {
 }
 
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cache[dev] == 0) {
+        int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+        cache[dev] = n > 0 ? n : 148;
     }
-    return n;
+    return cache[dev];
 }
 
 static SdfPointSource to_src(const rnb_points_t* p) {

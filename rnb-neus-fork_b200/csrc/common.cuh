@@ -168,6 +168,22 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N, uint32
     return (1u << 4) | (afmt << 7) | (bfmt << 10) | (amajor << 15) | (bmajor << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- host: opt-in dynamic shared memory
+// cudaFuncSetAttribute is per device and per kernel: remember which (kernel, device) pairs are done.  (One process
+// per GPU is the deployment, but nothing here may silently break with several devices in one process.)
+static inline cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
+    struct Key { const void* k; int dev; };
+    static Key done[64];
+    static int n_done = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < n_done; ++i)
+        if (done[i].k == kernel && done[i].dev == dev) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && n_done < 64) done[n_done++] = Key{kernel, dev};
+    return e;
+}
+
 // ---------------------------------------------------------------- small math
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);

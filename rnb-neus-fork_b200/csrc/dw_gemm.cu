@@ -296,11 +296,9 @@ cudaError_t launch_sum(const float* x, int64_t n, float* partial, float* out, cu
 }
 
 cudaError_t launch_dw_gemm(const DwParams& P, int splits, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)dw_gemm_kernel, DW_SMEM);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (P.n_jobs == 0) return cudaSuccess;
     dw_gemm_kernel<<<dim3(splits, P.n_jobs), DW_THREADS, DW_SMEM, st>>>(P);

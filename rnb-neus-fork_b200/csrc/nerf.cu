@@ -265,12 +265,10 @@ cudaError_t launch_nerf_pack(const float* const* W, const float* const* b, const
 }
 
 cudaError_t launch_nerf_fwd(const NerfFwdParams& P, int sm_count, cudaStream_t st) {
-    static bool attr = false;
     const int smem = chain_smem_bytes(NERF_A_COLS);
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(nerf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)nerf_fwd_kernel, smem);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (P.n_tiles == 0) return cudaSuccess;
     const int g = 2 * sm_count;

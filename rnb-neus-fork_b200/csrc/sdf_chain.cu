@@ -552,12 +552,10 @@ static inline int chain_grid(int n_tiles, int sm_count) {
 }
 
 cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st) {
-    static bool attr = false;
     const int smem = chain_smem_bytes(SDF_A_COLS);
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(sdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)sdf_fwd_kernel, smem);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (P.n_tiles == 0) return cudaSuccess;
     sdf_fwd_kernel<<<chain_grid(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
@@ -565,12 +563,10 @@ cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st)
 }
 
 cudaError_t launch_sdf_fwd_grad(const SdfFwdGradParams& P, int sm_count, cudaStream_t st) {
-    static bool attr = false;
     const int smem = chain_smem_bytes(SDF_A_COLS);
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(sdf_fwd_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)sdf_fwd_grad_kernel, smem);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (P.n_tiles == 0) return cudaSuccess;
     sdf_fwd_grad_kernel<<<chain_grid(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
@@ -578,12 +574,10 @@ cudaError_t launch_sdf_fwd_grad(const SdfFwdGradParams& P, int sm_count, cudaStr
 }
 
 cudaError_t launch_sdf_bwd_data(const SdfBwdParams& P, int sm_count, cudaStream_t st) {
-    static bool attr = false;
     const int smem = chain_smem_bytes(SDF_A_COLS);
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(sdf_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)sdf_bwd_data_kernel, smem);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     if (P.n_tiles == 0) return cudaSuccess;
     sdf_bwd_data_kernel<<<chain_grid(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
