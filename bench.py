@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dp8192", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (rnb_b200.graph_step)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -385,6 +386,16 @@ def main():
             return loss
 
         step = lambda i: train(dev_b[i % 4])
+        if args.graph:
+            from rnb_b200.graph_step import GraphedTrainStep
+            gs = GraphedTrainStep(renderer, params, lambda o, rgb, m: loss_fn(o, rgb, m), dev_b[0], warmup=True,
+                                  no_albedo=no_albedo, reducer=red)
+
+            def train(b):       # noqa: F811  (same contract: grads in the flat buffer, all-reduce outside the graph)
+                loss = gs(b)
+                red.all_reduce()
+                return loss
+            step = lambda i: train(dev_b[i % 4])
         for i in range(args.warmup):
             step(i)
         clk = ClockSampler(local)
@@ -461,7 +472,8 @@ def main():
                             peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})")
     line = dict(metric=metric_name(args.workload), value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate",
-                data="synthetic", config=dict(workload=wl["desc"], weights="geometric init, torch.manual_seed(0)",
+                data="synthetic", config=dict(workload=wl["desc"] + (" [one CUDA graph per step]" if getattr(args, "graph", False) else ""),
+                                              weights="geometric init, torch.manual_seed(0)",
                                               l2="per-step working set (activation streams, >1 GB) exceeds the 126 MB L2; "
                                                  "4 input batches rotate", parallelism=f"dp{world}"),
                 clocks=clocks, e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,

@@ -37,6 +37,12 @@ def packed_sdf_nograd(sdf_module):
     params = list(sdf_module.parameters())
     key = tuple((p.data_ptr(), p._version) for p in params)
     cache = getattr(sdf_module, "_rnb_packed", None)
+    if torch.cuda.is_current_stream_capturing():
+        # CUDA-graph capture (graph_step.py): the pack kernel must be PART of the graph, or replays after an
+        # optimiser step would sample with the weights of capture time
+        with torch.no_grad():
+            flat = _sdf_wb(sdf_module)
+            return _pack_sdf(flat, flat[0].device)
     if cache is None or cache[0] != key:
         with torch.no_grad():
             flat = _sdf_wb(sdf_module)
@@ -124,6 +130,9 @@ def packed_nerf(nerf_module):
     params = list(nerf_module.parameters())
     key = tuple((p.data_ptr(), p._version) for p in params)
     cache = getattr(nerf_module, "_rnb_packed", None)
+    if torch.cuda.is_current_stream_capturing():
+        with torch.no_grad():
+            return K.NerfPacked(nerf_module)
     if cache is None or cache[0] != key:
         with torch.no_grad():
             cache = (key, K.NerfPacked(nerf_module))

@@ -109,3 +109,35 @@ def test_no_grad_fast_path_matches_training_forward():
         for k in ("color_fine", "weights", "weight_sum", "weight_max", "gradients", "cdf_fine", "inside_sphere", "gradient_error"):
             assert torch.equal(out[k], ref[k].detach()), k
             assert not out[k].requires_grad
+
+
+def test_graphed_step_matches_eager():
+    """the whole step as one CUDA graph (launch-bound 512-ray regime): same loss and gradients as the eager step, also
+    after optimiser steps in between (the weight packing is part of the graph)"""
+    from rnb_b200.graph_step import GraphedTrainStep
+    from rnb_b200.parallel import FlatGradAllReducer
+    renderer, sdf, var, col = make_renderer(True)
+    renderer.perturb = 0.0                       # no jitter: eager and graphed steps must agree bit for bit
+    params = [p for m in (sdf, var, col) for p in m.parameters()]
+    red = FlatGradAllReducer(params)
+    opt = torch.optim.Adam(params, lr=1e-3)
+    lf = lambda out, rgb, mask: loss_fn(out, rgb, mask, 0.1)
+    gs = GraphedTrainStep(renderer, params, lf, batch(512, seed=2), warmup=True, reducer=red)
+    for seed in (3, 4, 5):
+        b = batch(512, seed=seed)
+        loss_g = gs(b).clone()
+        grads_g = red.flat.clone()
+        red.zero()
+        loss_e = lf(render(renderer, b), b["true_rgb"], b["mask"])
+        loss_e.backward()
+        assert torch.equal(loss_g, loss_e.detach())
+        assert torch.equal(grads_g, red.flat)
+        del loss_e                               # keep no eager autograd graph alive across captures / replays
+        opt.step()                               # parameters change in place: the next replay must see them
+    # with jitter every replay draws new random numbers
+    renderer.perturb = 1.0
+    gs2 = GraphedTrainStep(renderer, params, lf, batch(512, seed=2), warmup=True, reducer=red)
+    b = batch(512, seed=6)
+    l1 = gs2(b).clone()
+    l2 = gs2(b).clone()
+    assert torch.isfinite(l1) and torch.isfinite(l2) and not torch.equal(l1, l2)
