@@ -134,7 +134,8 @@ def build(device, geometric=True):
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, wl):
     """The path's CPU implementation on the box's host cores: the unmodified reference when /root/reference is
-    present (build container), else the numpy oracle port.  A bounded sample of the same workload per step."""
+    present (build container), else oracle/torch_port.py (same algorithm, float32 torch + autograd like the reference).
+    A bounded sample of the same workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -143,11 +144,11 @@ def run_reference(args, wl):
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     if args.workload == "grid512":
-        n_q = 32 ** 3
-        sample = f"{n_q} lattice queries (one 32^3 block) per step"
+        n_q = 64 ** 3
+        sample = f"{n_q} lattice queries (one 64^3 block, the reference's own block size) per step"
     else:
-        n_rays = 32
-        sample = f"{n_rays} rays of the workload per step (fwd + loss + bwd)"
+        n_rays = 512
+        sample = f"{n_rays} rays of the workload per step (the reference's own batch size; fwd + loss + bwd)"
     kind = "reference" if ref_loader.available() else "port"
     times = []
     if kind == "reference":
@@ -160,7 +161,7 @@ def run_reference(args, wl):
             t0 = time.perf_counter()
             if args.workload == "grid512":
                 with torch.no_grad():
-                    ref.renderer.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), 32, lambda p: -sdf.sdf(p))
+                    ref.renderer.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), 64, lambda p: -sdf.sdf(p))
             else:
                 b = synth.make_batch(n_rays, 3, True, 1, view=it)
                 for m in (sdf, var, col):
@@ -171,20 +172,24 @@ def run_reference(args, wl):
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
     else:
-        from oracle import rnb_oracle as O
+        # the reference tree is absent (GPU box): oracle/torch_port.py, the float32 torch + autograd restatement of the same
+        # algorithm (pinned against the reference's fixtures in tests/test_oracle_golden.py), on all host threads
+        from oracle import torch_port as T
         renderer, sdf, var, col = build("cpu")
-        sd = lambda m: {k: v.detach().double().numpy() for k, v in m.state_dict().items()}
-        sdf_sd, col_sd = sd(sdf), sd(col)
-        Ws, bs = O.sdf_effective(sdf_sd)
+        leaf = lambda m: {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        sdf_sd, col_sd = leaf(sdf), leaf(col)
+        variance = var.variance.detach().clone().requires_grad_(True)
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             if args.workload == "grid512":
-                O.extract_fields(Ws, bs, [-1.01] * 3, [1.01] * 3, 32)
+                T.extract_block(sdf_sd, [-1.01] * 3, [1.01] * 3, 64)
             else:
-                b = {k: v.numpy() for k, v in synth.make_batch(n_rays, 3, True, 1, view=it).items()}
-                ret, cache = O.render_rnb(sdf_sd, col_sd, 0.3, b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
-                                          b["t_rand"], 1.0, True, wl["no_albedo"])
-                O.train_step_grads(ret, cache, b["true_rgb"], b["mask"])
+                b = synth.make_batch(n_rays, 3, True, 1, view=it)
+                for t in list(sdf_sd.values()) + list(col_sd.values()) + [variance]:
+                    t.grad = None
+                out = T.render_rnb(sdf_sd, col_sd, variance, b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
+                                   b["t_rand"], 1.0, True, wl["no_albedo"])
+                T.loss_fn(out, b["true_rgb"], b["mask"]).backward()
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))
@@ -193,7 +198,7 @@ def run_reference(args, wl):
     unit = "SDF queries/s" if args.workload == "grid512" else "rays/s"
     line = dict(impl="reference", metric=metric_name(args.workload), value=val, unit=unit, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32" if kind == "reference" else "f64", data="synthetic",
+                dtype="f32", data="synthetic",
                 config=dict(workload=wl["desc"], sample=sample),
                 cpu_baseline=dict(value=val, unit=unit, cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)

@@ -198,3 +198,30 @@ def test_background_render():
     # the outside samples lie beyond every inside sample: sort(cat) == cat, which the merge kernel relies on only
     # for speed (it is a general two-list rank merge)
     assert np.all(np.diff(g["z_feed"], axis=-1) >= 0)
+
+
+@pytest.mark.parametrize("case", ["warmup_albedo", "post_noalbedo"])
+def test_torch_port_against_reference_fixtures(case):
+    """oracle/torch_port.py (the CPU arm of bench.py where the reference tree is absent) reproduces the reference's own
+    outputs, loss and parameter gradients: same algorithm, same float32 autograd"""
+    from oracle import torch_port as T
+    g = load_golden("render_" + case)
+    _, _, _, _, (sdf, col, var) = ref_like_state_dicts(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    sdf_sd = {k: v.detach().clone().requires_grad_(True) for k, v in sdf.state_dict().items()}
+    col_sd = {k: v.detach().clone().requires_grad_(True) for k, v in col.state_dict().items()}
+    variance = var.variance.detach().clone().requires_grad_(True)
+    out = T.render_rnb(sdf_sd, col_sd, variance, t(g["rays_o"]), t(g["rays_d"]), t(g["near"]), t(g["far"]), t(g["lights_dir"]),
+                       t(g["t_rand"]), float(g["r"]), bool(g["warmup"]), bool(g["no_albedo"]))
+    for k in ("color_fine", "weight_sum", "gradients"):
+        assert rel_l2(out[k].detach().numpy(), g["out_" + k]) < 1e-4, k
+    # individual sample weights amplify float32 round-off of the SDF by inv_s/10 (ray sums do not): see DESIGN.md section 5
+    for k in ("weights", "cdf_fine"):
+        assert rel_l2(out[k].detach().numpy(), g["out_" + k]) < 5e-3, k
+    loss = T.loss_fn(out, t(g["true_rgb"]), t(g["mask_used"]), 0.1, float(g["mask_weight"]))
+    assert abs(float(loss) / float(g["loss"]) - 1) < 1e-4
+    loss.backward()
+    stride = int(g["stride"])
+    for name, p in sorted(sdf_sd.items()):
+        got = p.grad.detach().numpy().reshape(-1)[::stride]
+        assert rel_l2(got, g["g_sdf." + name]) < 5e-3, name
