@@ -174,3 +174,30 @@ def test_device_ray_batcher_matches_reference_expressions():
     mid = 0.5 * (-b) / a
     assert torch.allclose(out["near"].cpu(), mid - 1.0, atol=1e-5) and torch.allclose(out["far"].cpu(), mid + 1.0, atol=1e-5)
     assert torch.equal(out["lights_dir"].cpu(), lights[v, :, pixels_y, pixels_x, :].reshape(Lh, B, 1, 3))
+
+
+def test_plain_render_without_background_model():
+    """NeuSRenderer.render (reference models/renderer.py:556-648) with n_outside = 0: colour = sum_i w_i c_i
+    (+ background_rgb (1 - sum w)), against the float64 oracle on the same sample depths"""
+    from gpu_common import np_state
+    from oracle import rnb_oracle as O
+    from models.renderer import NeuSRenderer
+    nerf, sdf, var, col = build_nets(True)
+    r = NeuSRenderer(nerf, sdf, var, col, **synth.WMASK_CONF["neus_renderer"])
+    r.color_depth = 3
+    b = {k: v.cuda() for k, v in synth.make_batch(96, 3, True, 4).items()}
+    bg = torch.ones(1, 3, device="cuda")
+    torch.manual_seed(21)
+    out = r.render(b["rays_o"], b["rays_d"], b["near"], b["far"], cos_anneal_ratio=0.7, background_rgb=bg)
+    torch.manual_seed(21)
+    z_vals, _ = r._sample(b["rays_o"], b["rays_d"], b["near"], b["far"], -1)       # the depths render() just used
+    c = lambda t: t.detach().cpu().numpy()
+    ret, cache = O.render_rnb(np_state(sdf), np_state(col), float(var.variance), c(b["rays_o"]), c(b["rays_d"]), c(b["near"]),
+                              c(b["far"]), c(b["lights_dir"]), None, 0.7, True, False, z_vals=c(z_vals))
+    w = cache["fw"]["weights"]
+    expect = (w[:, :, None] * cache["albedo"]).sum(1) + (1.0 - w.sum(-1, keepdims=True))
+    assert tuple(out["color_fine"].shape) == (96, 3)
+    assert rel_l2(c(out["color_fine"]), expect) < 1e-3
+    assert rel_l2(c(out["weight_sum"]), ret["weight_sum"]) < 1e-3
+    assert abs(float(out["gradient_error"]) / float(ret["gradient_error"]) - 1) < 1e-3
+    assert rel_l2(c(out["gradients"]), ret["gradients"]) < 1e-3
