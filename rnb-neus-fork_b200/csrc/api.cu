@@ -52,7 +52,7 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
     const int64_t n_pad = rnb_padded_points(n_pts);
     const int n_sub = (int)(n_pad / 64);
     L.dw_splits = std::max(1, std::min(n_sub, 96));
-    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 32));
+    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 96));
     size_t o = 0;
     L.absmax = o; o += 256;
     L.sum_part = o; o += 3 * 256;
@@ -77,7 +77,7 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     const size_t s256 = rnb_stream_bytes(n_pts, 256), s64 = rnb_stream_bytes(n_pts, 64);
     const int n_sub = (int)(rnb_padded_points(n_pts) / 64);
     L.dw_splits = std::max(1, std::min(n_sub, 48));
-    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 32));
+    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 96));
     size_t o = 0;
     L.absmax = o; o += 256;
     L.sum_part = o; o += 256;
@@ -322,7 +322,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     float* cpart = (float*)(sc + L.cs_part);
     auto add_cs = [&](const uint8_t* stream, const float* wgt) {
         ColsumJob& j = C.jobs[C.n_jobs++];
-        j.stream = stream; j.chunks = 32; j.row_weight = wgt; j.partial = cpart;
+        j.stream = stream; j.chunks = 32; j.n_w = 1; j.row_weight[0] = wgt; j.partial[0] = cpart;
         float* p0 = cpart;
         cpart += (size_t)L.cs_splits * 256;
         return p0;
@@ -503,15 +503,19 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     C.n_sub = n_sub;
     C.n_pts = n_pad;
     float* cpart = (float*)(sc + L.cs_part);
-    auto add_cs = [&](const uint8_t* stream, const float* wgt, float* dst, int use_scale) {
+    {
+        // dW_2[k,:] = sum_p dz2[k,p] h1[p,:], k = 0..2: three weighted column sums in ONE pass over the h1 stream
         ColsumJob& j = C.jobs[C.n_jobs++];
-        j.stream = stream; j.chunks = 32; j.row_weight = wgt; j.partial = cpart;
-        ReduceJob& r = R.jobs[R.n_jobs++];
-        r.partial = cpart; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
-        r.dst = dst; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = use_scale;
-        cpart += (size_t)L.cs_splits * 256;
-    };
-    for (int k = 0; k < 3; ++k) add_cs((const uint8_t*)st_h1, P.dz2 + (size_t)k * n_pad, dW2 + k * 256, 0);
+        j.stream = (const uint8_t*)st_h1; j.chunks = 32; j.n_w = 3;
+        for (int k = 0; k < 3; ++k) {
+            j.row_weight[k] = P.dz2 + (size_t)k * n_pad;
+            j.partial[k] = cpart;
+            ReduceJob& r = R.jobs[R.n_jobs++];
+            r.partial = cpart; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
+            r.dst = dW2 + k * 256; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = 0;
+            cpart += (size_t)L.cs_splits * 256;
+        }
+    }
     e = profiled(T_COLSUM, st, [&] { return launch_colsum(C, L.cs_splits, st); });
     if (e != cudaSuccess) return (int)e;
     e = profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });

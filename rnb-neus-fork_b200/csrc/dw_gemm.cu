@@ -176,36 +176,49 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ Col
     const int per = (P.n_sub + (int)gridDim.y - 1) / (int)gridDim.y;
     const int sub0 = split * per, sub1 = min(P.n_sub, sub0 + per);
     const int r = threadIdx.x & 63, sl = threadIdx.x >> 6;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float acc[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+#pragma unroll 4
     for (int sub = sub0 + sl; sub < sub1; sub += 4) {
         const uint4 u = *reinterpret_cast<const uint4*>(job.stream + (((size_t)sub * job.chunks + chunk) * 64 + r) * 16);
-        float wgt = 1.f;
-        if (job.row_weight) {
-            const int64_t p = (int64_t)sub * 64 + r;
-            wgt = p < P.n_pts ? __ldg(job.row_weight + p) : 0.f;
+        const int64_t p = (int64_t)sub * 64 + r;
+        float wgt[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            wgt[k] = k < job.n_w ? 1.f : 0.f;
+            if (k < job.n_w && job.row_weight[k]) wgt[k] = p < P.n_pts ? __ldg(job.row_weight[k] + p) : 0.f;
         }
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 f = unpack_h2(w[j]);
-            acc[2 * j] = fmaf(wgt, f.x, acc[2 * j]);
-            acc[2 * j + 1] = fmaf(wgt, f.y, acc[2 * j + 1]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[k][2 * j] = fmaf(wgt[k], f.x, acc[k][2 * j]);
+                acc[k][2 * j + 1] = fmaf(wgt[k], f.y, acc[k][2 * j + 1]);
+            }
         }
     }
-    __shared__ float red[8][8];
+    __shared__ float red[3][8][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float v = acc[j];
+    for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = v;
-    }
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[k][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5][j] = v;
+        }
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if (threadIdx.x < 8 * job.n_w) {
+        const int k = threadIdx.x >> 3, j = threadIdx.x & 7;
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-        job.partial[(size_t)split * job.chunks * 8 + chunk * 8 + threadIdx.x] = v;
+        for (int w = 0; w < 8; ++w) v += red[k][w][j];
+        job.partial[k][(size_t)split * job.chunks * 8 + chunk * 8 + j] = v;
     }
 }
 

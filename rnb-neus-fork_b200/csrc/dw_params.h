@@ -27,8 +27,9 @@ struct DwParams {
 struct ColsumJob {
     const uint8_t* stream;
     int chunks;               // stream width / 8
-    const float* row_weight;  // optional per-point weight (fp32 [n_pts]); null = 1
-    float* partial;           // [splits][chunks*8]
+    int n_w;                  // 1..3 weighted sums taken in ONE pass over the stream
+    const float* row_weight[3];   // optional per-point weights (fp32 [n_pts]); null = 1
+    float* partial[3];            // each [splits][chunks*8]
 };
 struct ColsumParams {
     int n_jobs;
