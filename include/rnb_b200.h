@@ -175,6 +175,16 @@ typedef struct {
 } rnb_ray_batch_t;
 RNB_API int rnb_ray_batch(const rnb_ray_batch_t* p, void* stream);
 
+/* ---- marching cubes on the device lattice (reference models/renderer.py:28-36 calls PyMCubes on the
+ *      host after copying the whole lattice).  u: fp32 [nx,ny,nz] C-contiguous, inside = u > threshold.  Two passes:
+ *      rnb_mc_count -> counts[(nx-1)(ny-1)(nz-1)] triangles per cell; the caller scans them into offsets;
+ *      rnb_mc_emit  -> verts [n_tri*3,3] in lattice index coordinates (x shifted by x_global0 for slabs) and
+ *      keys [n_tri*3] identifying the cube edge of every vertex (equal key <=> same vertex: weld with a unique).
+ *      tri_count [256] / tri_table [256*16] (int8, device) come from rnb_b200/mc_tables.py. ----------------------- */
+RNB_API int rnb_mc_count(const float* u, int nx, int ny, int nz, float threshold, const int8_t* tri_count, int32_t* counts, void* stream);
+RNB_API int rnb_mc_emit(const float* u, int nx, int ny, int nz, float threshold, const int8_t* tri_table, const int64_t* offsets,
+                int x_global0, float* verts, int64_t* keys, void* stream);
+
 /* fp32 [n, cols] row-major -> fp16 stream image (cols % 8 == 0; out: rnb_stream_bytes(n, cols)).  Used by the
  * stand-alone RenderingNetwork.forward (exp_runner.py:613-615 validate_mesh_texture), whose feature vectors arrive
  * as an fp32 tensor instead of the stream rnb_sdf_fwd_grad writes. */

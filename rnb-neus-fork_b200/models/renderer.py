@@ -28,10 +28,22 @@ def extract_fields(bound_min, bound_max, resolution, query_func=None, sdf_networ
 
 
 def extract_geometry(bound_min, bound_max, resolution, threshold, query_func=None, sdf_network=None):
-    """reference :28-36 -- marching cubes stays on the host."""
+    """reference :28-36.  With PyMCubes installed: the reference's flow (lattice to the host, `mcubes.marching_cubes`).
+    Without it (or with RNB_DEVICE_MC=1): the lattice never leaves the GPU -- `rnb_b200.grid.marching_cubes_device`
+    extracts the triangles from the device slab (same vertex placement on lattice edges)."""
+    import os
     print('threshold: {}'.format(threshold))
-    u = extract_fields(bound_min, bound_max, resolution, query_func, sdf_network)
-    vertices, triangles = _grid.marching_cubes(u, threshold)
+    try:
+        import mcubes  # noqa: F401
+        have_mcubes = True
+    except ImportError:
+        have_mcubes = False
+    if sdf_network is not None and (not have_mcubes or os.environ.get("RNB_DEVICE_MC") == "1"):
+        u_dev = _grid.sdf_slab(sdf_network, bound_min, bound_max, resolution, 0, resolution)
+        vertices, triangles = _grid.marching_cubes_device(u_dev, threshold)
+    else:
+        u = extract_fields(bound_min, bound_max, resolution, query_func, sdf_network)
+        vertices, triangles = _grid.marching_cubes(u, threshold)
     b_max_np = bound_max.detach().cpu().numpy()
     b_min_np = bound_min.detach().cpu().numpy()
     vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]

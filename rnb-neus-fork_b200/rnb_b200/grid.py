@@ -76,11 +76,66 @@ def extract_fields_callable(bound_min, bound_max, resolution, query_func):
     return u
 
 
+_MC_TABLES = {}
+
+
+def _mc_tables(device):
+    key = str(device)
+    if key not in _MC_TABLES:
+        from . import mc_tables as M
+        _MC_TABLES[key] = (torch.from_numpy(M.TRI_COUNT.astype(np.int8)).to(device),
+                           torch.from_numpy(np.ascontiguousarray(M.TRI_TABLE)).to(device))
+    return _MC_TABLES[key]
+
+
+@torch.no_grad()
+def marching_cubes_device(u, threshold, x_global0=0, weld=True):
+    """Marching cubes on a device lattice u [nx,ny,nz] (inside = u > threshold), no host copy of the lattice
+    (SURVEY 8f rank 3).  -> (vertices float64 [V,3] in lattice index coordinates, triangles int64 [T,3]) as numpy, the
+    return convention of `mcubes.marching_cubes` (reference models/renderer.py:31).  With weld=False returns the raw
+    device tensors (verts [T*3,3] float32, keys [T*3] int64) for merging slabs before one global weld."""
+    import ctypes as C
+    L.require_cuda(u, "marching_cubes_device")
+    u = u.detach().float().contiguous()
+    nx, ny, nz = u.shape
+    dev = u.device
+    n_cells = max(nx - 1, 0) * max(ny - 1, 0) * max(nz - 1, 0)
+    tri_count, tri_table = _mc_tables(dev)
+    counts = torch.empty(n_cells, dtype=torch.int32, device=dev)
+    lib = L.load()
+    L.check(lib.rnb_mc_count(L.ptr(u), nx, ny, nz, float(threshold), L.ptr(tri_count), L.ptr(counts), L.stream_ptr()), "mc_count")
+    incl = torch.cumsum(counts, 0, dtype=torch.int64)
+    n_tri = int(incl[-1]) if n_cells else 0                       # the one host sync: the output size
+    offsets = (incl - counts).contiguous()
+    verts = torch.empty(n_tri * 3, 3, dtype=torch.float32, device=dev)
+    keys = torch.empty(n_tri * 3, dtype=torch.int64, device=dev)
+    if n_tri:
+        L.check(lib.rnb_mc_emit(L.ptr(u), nx, ny, nz, float(threshold), L.ptr(tri_table), L.ptr(offsets), int(x_global0),
+                                L.ptr(verts), L.ptr(keys), L.stream_ptr()), "mc_emit")
+    if not weld:
+        return verts, keys
+    return weld_mesh(verts, keys)
+
+
+@torch.no_grad()
+def weld_mesh(verts, keys):
+    """Merge vertices that lie on the same lattice edge (equal key): -> (vertices float64 [V,3], triangles int64 [T,3])"""
+    if keys.numel() == 0:
+        return np.zeros((0, 3), np.float64), np.zeros((0, 3), np.int64)
+    uniq, inverse = torch.unique(keys, return_inverse=True)
+    out = torch.empty(uniq.numel(), 3, dtype=verts.dtype, device=verts.device)
+    out[inverse] = verts                                           # duplicates carry identical coordinates
+    return out.double().cpu().numpy(), inverse.view(-1, 3).cpu().numpy()
+
+
 def marching_cubes(u, threshold):
-    """Host marching cubes.  PyMCubes (the reference's dependency, README.md:36) when installed."""
+    """Marching cubes of a host lattice.  PyMCubes (the reference's dependency, README.md:36) when installed, else the
+    device extractor of this library (same vertex placement on lattice edges; triangle order and the triangulation of
+    individual cells may differ -- PyMCubes is absent from every environment of this build, so parity with it is unpinned)."""
     try:
         import mcubes
-    except ImportError as e:
-        raise RuntimeError("rnb_b200: PyMCubes is not installed; the SDF lattice `u` (extract_fields) is the boundary "
-                           "of the B200 path -- install PyMCubes for the host marching-cubes step") from e
+    except ImportError:
+        if not torch.cuda.is_available():
+            raise RuntimeError("rnb_b200: neither PyMCubes nor a CUDA device is available for marching cubes")
+        return marching_cubes_device(torch.as_tensor(u, device="cuda"), threshold)
     return mcubes.marching_cubes(u, threshold)

@@ -96,6 +96,8 @@ _SIGNATURES = {
     "rnb_nerf_pack": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP)] + [_VP] * 11),
     "rnb_nerf_fwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 7),
     "rnb_composite_bg_fwd": (C.c_int, [C.POINTER(CompositeBg), _VP]),
+    "rnb_mc_count": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
+    "rnb_mc_emit": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, C.c_int, _VP, _VP, _VP]),
     "rnb_ray_batch": (C.c_int, [C.POINTER(RayBatch), _VP]),
     "rnb_stream_from_rowmajor": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP]),
     "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 11 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),
