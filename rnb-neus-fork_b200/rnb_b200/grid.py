@@ -128,6 +128,57 @@ def weld_mesh(verts, keys):
     return out.double().cpu().numpy(), inverse.view(-1, 3).cpu().numpy()
 
 
+@torch.no_grad()
+def gather_and_weld(verts, keys, group=None):
+    """Rank 0 receives every rank's raw triangles (verts [n,3], keys [n]; n differs per rank), welds them once with the
+    global edge keys and returns (vertices, triangles); other ranks return None.  The only collectives of the sharded
+    mesh extraction: one all_gather of the sizes, one gather of the padded triangle soup (a few MB, not the lattice)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = torch.tensor([keys.numel()], dtype=torch.int64, device=keys.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(t) for t in sizes]
+    cap = max(max(sizes), 1)
+    pv = torch.zeros(cap, 3, dtype=verts.dtype, device=verts.device)
+    pk = torch.zeros(cap, dtype=torch.int64, device=keys.device)
+    pv[:keys.numel()] = verts
+    pk[:keys.numel()] = keys
+    gv = [torch.empty_like(pv) for _ in range(world)] if rank == 0 else None
+    gk = [torch.empty_like(pk) for _ in range(world)] if rank == 0 else None
+    dist.gather(pv, gv, dst=0, group=group)
+    dist.gather(pk, gk, dst=0, group=group)
+    if rank != 0:
+        return None
+    return weld_mesh(torch.cat([v[:m] for v, m in zip(gv, sizes)]), torch.cat([k[:m] for k, m in zip(gk, sizes)]))
+
+
+@torch.no_grad()
+def extract_mesh_distributed(sdf_network, bound_min, bound_max, resolution, threshold=0.0, group=None):
+    """validate_mesh sharded over the ranks of one box without ever gathering the lattice: rank r evaluates the x-slab
+    [x0_r, x1_r] (one plane of overlap closes the cells between slabs), runs marching cubes on it on its own GPU, and only
+    the triangles travel.  -> (vertices float64 [V,3] in world coordinates, triangles [T,3]) on rank 0, None elsewhere
+    (the return convention of extract_geometry, reference models/renderer.py:28-36)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    x0, x1 = slab_bounds(resolution, rank, world)
+    dev = next(sdf_network.parameters()).device
+    if x1 > x0:
+        xe = min(x1 + 1, resolution)
+        u = sdf_slab(sdf_network, bound_min, bound_max, resolution, x0, xe)
+        verts, keys = marching_cubes_device(u, threshold, x_global0=x0, weld=False)
+    else:
+        verts = torch.zeros(0, 3, dtype=torch.float32, device=dev)
+        keys = torch.zeros(0, dtype=torch.int64, device=dev)
+    out = gather_and_weld(verts, keys, group)
+    if out is None:
+        return None
+    vertices, triangles = out
+    bmin = torch.as_tensor(bound_min).detach().cpu().double().numpy().reshape(-1)
+    bmax = torch.as_tensor(bound_max).detach().cpu().double().numpy().reshape(-1)
+    return vertices / (resolution - 1.0) * (bmax - bmin)[None, :] + bmin[None, :], triangles
+
+
 def marching_cubes(u, threshold):
     """Marching cubes of a host lattice.  PyMCubes (the reference's dependency, README.md:36) when installed, else the
     device extractor of this library (same vertex placement on lattice edges; triangle order and the triangulation of

@@ -190,3 +190,70 @@ def test_data_parallel_allreduce_gloo_world2():
     loss.backward()
     ref = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy()
     assert np.allclose(res[0][1], ref, atol=1e-6)
+
+
+def _cpu_triangle_soup(u, x_lo, x_hi):
+    """marching cubes with the generated tables on the cells x_lo <= x < x_hi of a small host lattice (test helper)"""
+    from rnb_b200 import mc_tables as M
+    nx, ny, nz = u.shape
+    verts, keys = [], []
+    for x in range(x_lo, x_hi):
+        for y in range(ny - 1):
+            for z in range(nz - 1):
+                case = sum(1 << i for i, (ox, oy, oz) in enumerate(M.CORNER_OFFSETS) if u[x + ox, y + oy, z + oz] > 0)
+                for e in M.TRI_TABLE[case][:3 * M.TRI_COUNT[case]]:
+                    a, b = M.EDGE_CORNERS[e]
+                    pa, pb = np.array([x, y, z]) + M.CORNER_OFFSETS[a], np.array([x, y, z]) + M.CORNER_OFFSETS[b]
+                    t = (0.0 - u[tuple(pa)]) / (u[tuple(pb)] - u[tuple(pa)])
+                    verts.append(pa + t * (pb - pa))
+                    keys.append(((pa[0] * ny + pa[1]) * nz + pa[2]) * 3 + int(e) // 4)
+    return torch.tensor(np.array(verts).reshape(-1, 3), dtype=torch.float32), torch.tensor(keys, dtype=torch.int64)
+
+
+def _mesh_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "rnb-neus-fork_b200"))
+    from rnb_b200 import grid
+    n = 12
+    g = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    u = 0.6 - np.sqrt(X ** 2 + Y ** 2 + Z ** 2)
+    x0, x1 = grid.slab_bounds(n, rank, world)
+    verts, keys = _cpu_triangle_soup(u, x0, min(x1, n - 1))       # cells of this rank's slab (the overlap plane closes the seam)
+    out = grid.gather_and_weld(verts, keys)
+    q.put((rank, None if out is None else (out[0], out[1])))
+    dist.destroy_process_group()
+
+
+def test_sharded_mesh_gather_and_weld_gloo_world2():
+    """slab-wise marching cubes + one gather of the triangles == one pass over the whole lattice (closed, genus 0)"""
+    import torch.multiprocessing as mp
+    from collections import Counter
+    sys.path.insert(0, os.path.join(ROOT, "rnb-neus-fork_b200"))
+    from rnb_b200 import grid
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_mesh_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[1] is None
+    V, T = res[0]
+    n = 12
+    g = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    Vs, Ts = grid.weld_mesh(*_cpu_triangle_soup(0.6 - np.sqrt(X ** 2 + Y ** 2 + Z ** 2), 0, n - 1))
+    assert V.shape == Vs.shape and T.shape == Ts.shape
+    de = Counter()
+    for a, b, c in T:
+        for e in ((a, b), (b, c), (c, a)):
+            de[e] += 1
+    und = Counter(tuple(sorted(e)) for e in de)
+    assert max(de.values()) == 1 and set(und.values()) == {2} and len(V) - len(und) + len(T) == 2
