@@ -210,10 +210,6 @@ struct Epi {
     __device__ __forceinline__ float* xchg() const {
         return reinterpret_cast<float*>(sA + ((size_t)8 * TILE_M + row) * 16);
     }
-    __device__ __forceinline__ void ld_acc(int c0, uint32_t (&v)[32]) const {
-        tmem_ld32(tmem_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-    }
     __device__ __forceinline__ void ld_acc16(int c0, uint32_t (&v)[16]) const {
         tmem_ld16(tmem_row + (uint32_t)c0, v);
         tmem_ld_wait16(v);
@@ -296,11 +292,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -324,14 +315,6 @@ __device__ __forceinline__ float softplus100(float z) {
     const float q = ex2_approx(-144.26950408889634f * fabsf(z));
     return fmaf(q, softplus100_corr(q), fmaxf(z, 0.f));
 }
-// a = softplus(z), s = softplus'(z) = sigmoid(100 z)
-__device__ __forceinline__ void softplus100_ds(float z, float& a, float& s) {
-    const float e = ex2_approx(-144.26950408889634f * fabsf(z));
-    const float r = rcp_approx(1.f + e);
-    a = fmaf(e, softplus100_corr(e), fmaxf(z, 0.f));
-    s = z >= 0.f ? r : e * r;
-}
-
 // softplus'(z) recovered from a = softplus(z):  a = log(1 + e^{100 z}) / 100  =>  sigmoid(100 z) = 1 - e^{-100 a}.
 // Lets the backward kernels read the activation stream they need anyway instead of a separate s stream.
 __device__ __forceinline__ float sig_from_a(float a) { return 1.f - ex2_approx(-144.26950408889634f * a); }

@@ -77,17 +77,6 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
-// shared -> global
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
 // pull a contiguous global range into L2 ahead of use (no destination, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
@@ -248,15 +237,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
     return __half22float2(*reinterpret_cast<__half2*>(&u));
-}
-__device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
 }  // namespace rnb
