@@ -321,6 +321,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from rnb_b200 import synth, lib as L, grid
     from rnb_b200.parallel import FlatGradAllReducer
+    from rnb_b200.optim import FlatAdam
 
     renderer, sdf, var, col = build(dev)
     pk = peaks()
@@ -376,7 +377,7 @@ def main():
         no_albedo = wl["no_albedo"]
         params = list(sdf.parameters()) + list(var.parameters()) + ([] if no_albedo else list(col.parameters()))
         red = FlatGradAllReducer(params)
-        opt = torch.optim.Adam(params, lr=5e-4, fused=True)
+        opt = FlatAdam(params, lr=5e-4, reducer=red)   # one launch over the flat buffers the all-reduce uses
         host_b = [{k: v.pin_memory() for k, v in synth.make_batch(B, 3, True, 1 + rank, view=i).items()} for i in range(4)]
         dev_b = [{k: v.to(dev) for k, v in hb.items()} for hb in host_b]
         keys = ("rays_o", "rays_d", "near", "far", "lights_dir", "true_rgb", "mask")
@@ -422,8 +423,7 @@ def main():
         def full_step(i):
             step(i)
             opt.step()
-        for i in range(2):                          # Adam allocates its state on the first call
-            full_step(i)
+        full_step(0)
         ms_full = timed(full_step, max(3, args.steps // 2))
         units = B * world
         h2d = sum(host_b[0][k].numel() * 4 for k in keys)

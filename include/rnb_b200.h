@@ -175,6 +175,13 @@ typedef struct {
 } rnb_ray_batch_t;
 RNB_API int rnb_ray_batch(const rnb_ray_batch_t* p, void* stream);
 
+/* ---- step epilogue (reference exp_runner.py:115 torch.optim.Adam over 61 parameter tensors, :263
+ *      optimizer.step()).  One launch over flat fp32 buffers of n elements (16-byte aligned): param, grad, exp_avg and
+ *      exp_avg_sq, torch.optim.Adam arithmetic with amsgrad off and weight_decay 0; `step` is the 1-based step count
+ *      of this update, grad is multiplied by grad_scale first (1/world after a summing all-reduce). -------------------- */
+RNB_API int rnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, double grad_scale, void* stream);
+
 /* ---- marching cubes on the device lattice (reference models/renderer.py:28-36 calls PyMCubes on the
  *      host after copying the whole lattice).  u: fp32 [nx,ny,nz] C-contiguous, inside = u > threshold.  Two passes:
  *      rnb_mc_count -> counts[(nx-1)(ny-1)(nz-1)] triangles per cell; the caller scans them into offsets;

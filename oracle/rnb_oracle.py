@@ -725,3 +725,29 @@ def render_plain_background(sdf_sd, color_sd, nerf_sd, variance, rays_o, rays_d,
     return dict(color_fine=c, weights=w, weight_sum=wsum, weight_max=w.max(-1, keepdims=True),
                 cdf_fine=fw["cdf_fine"], inside_sphere=inside, gradient_error=fw["gradient_error"],
                 gradients=g.reshape(B, n, 3), s_val=fw["s_val"], bg_alpha=bg_alpha, bg_color=bg_color)
+
+
+# --------------------------------------------------------------------------
+# 8f-2  step epilogue: Adam + learning-rate schedule   exp_runner.py:115, 263, 320-332
+# --------------------------------------------------------------------------
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """One torch.optim.Adam update (amsgrad off, weight_decay 0: what exp_runner.py:115 constructs), `step` = 1-based
+    count of this update.  Returns the new (p, m, v); float64."""
+    p, g, m, v = (np.asarray(a, F64) for a in (p, g, m, v))
+    m = m + (g - m) * (1.0 - beta1)
+    v = v * beta2 + (1.0 - beta2) * g * g
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    denom = np.sqrt(v) / np.sqrt(bc2) + eps
+    return p - (lr / bc1) * (m / denom), m, v
+
+
+def learning_rate(iter_step, base_lr=5e-4, alpha=0.05, warm_up_end=5000, end_iter=300000):
+    """exp_runner.py:320-332 (defaults: confs/wmask_rnb.conf:21-23, 28)."""
+    if iter_step < warm_up_end:
+        f = iter_step / warm_up_end
+    else:
+        progress = (iter_step - warm_up_end) / (end_iter - warm_up_end)
+        f = (np.cos(np.pi * progress) + 1.0) * 0.5 * (1 - alpha) + alpha
+    return base_lr * f

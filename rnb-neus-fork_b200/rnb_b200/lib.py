@@ -98,6 +98,8 @@ _SIGNATURES = {
     "rnb_composite_bg_fwd": (C.c_int, [C.POINTER(CompositeBg), _VP]),
     "rnb_mc_count": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
     "rnb_mc_emit": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, C.c_int, _VP, _VP, _VP]),
+    "rnb_adam_step": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                C.c_int64, C.c_double, _VP]),
     "rnb_ray_batch": (C.c_int, [C.POINTER(RayBatch), _VP]),
     "rnb_stream_from_rowmajor": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP]),
     "rnb_sdf_bwd": (C.c_int, [C.POINTER(Points)] + [_VP] * 11 + [C.POINTER(_VP), C.POINTER(_VP), _VP]),

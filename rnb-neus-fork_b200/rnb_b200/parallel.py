@@ -13,18 +13,19 @@ import torch.distributed as dist
 
 
 class FlatGradAllReducer:
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, align=4):
+        """align: every parameter's slice starts at a multiple of `align` floats (16 bytes by default, so slices keep
+        the alignment vector loads need); the padding stays zero."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
-        n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets = []
         o = 0
-        self.views = []
         for p in self.params:
-            v = self.flat[o:o + p.numel()].view_as(p)
-            self.views.append(v)
-            o += p.numel()
+            self.offsets.append(o)
+            o += -(-p.numel() // align) * align
+        dev = self.params[0].device
+        self.flat = torch.zeros(o, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
         self.attach()
 
     def attach(self):
