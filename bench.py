@@ -417,7 +417,7 @@ def main():
             hb = host_b[i % 4]
             b = {k: hb[k].to(dev, non_blocking=True) for k in keys}
             loss = train(b)
-            return float(loss)                       # device -> host read of the step's result
+            return float(loss.detach())              # device -> host read of the step's result
         ms_e2e = timed(e2e_step, args.steps)
 
         def full_step(i):
