@@ -26,12 +26,35 @@ class DeviceRayBatcher:
         L.require_cuda(self.images, "DeviceRayBatcher")
         self.n_images, self.n_lights, self.H, self.W = self.images.shape[:4]
         self.device = self.images.device
+        self._pix_ring, self._pix_slot = [], 0
+
+    def _pixels_to_device(self, pixels_x, pixels_y):
+        """CPU pixel indices (the reference draws them with the CPU generator) -> device, without blocking the host: a
+        pageable-memory copy would make every iteration wait for the GPU to drain; a small ring of pinned staging
+        buffers, each guarded by the event of its last copy, keeps the launch queue running ahead."""
+        B = pixels_x.numel()
+        if not self._pix_ring or self._pix_ring[0][0].shape[1] != B:
+            self._pix_ring = [(torch.empty(2, B, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._pix_slot = 0
+            for _, ev in self._pix_ring:
+                ev.record()
+        host, ev = self._pix_ring[self._pix_slot]
+        self._pix_slot = (self._pix_slot + 1) % len(self._pix_ring)
+        ev.synchronize()
+        host[0].copy_(pixels_x)
+        host[1].copy_(pixels_y)
+        d = host.to(self.device, non_blocking=True)
+        ev.record()
+        return d[0], d[1]
 
     def gather(self, img_idx, pixels_x, pixels_y, want_lights=True):
         """-> dict(rays_o, rays_d [B,3], near, far, mask [B,1], images_warmup, images [L,B,3], lights_dir [L,B,1,3])"""
         dev = self.device
-        px = pixels_x.to(dev, torch.int64).contiguous()
-        py = pixels_y.to(dev, torch.int64).contiguous()
+        if not pixels_x.is_cuda and not pixels_y.is_cuda and pixels_x.dim() == 1 and pixels_x.shape == pixels_y.shape:
+            px, py = self._pixels_to_device(pixels_x, pixels_y)
+        else:
+            px = pixels_x.to(dev, torch.int64).contiguous()
+            py = pixels_y.to(dev, torch.int64).contiguous()
         B = px.numel()
         f32 = dict(dtype=torch.float32, device=dev)
         out = dict(rays_o=torch.empty(B, 3, **f32), rays_d=torch.empty(B, 3, **f32), near=torch.empty(B, 1, **f32),
