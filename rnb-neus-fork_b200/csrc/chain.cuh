@@ -18,8 +18,12 @@
 namespace rnb {
 
 constexpr int TILE_M = 128;
-constexpr int RING_STAGES = 3;
-constexpr int STAGE_BYTES = 16384;        // K=32 slice of a 256-row operand
+#ifndef RNB_SLICE_K
+#define RNB_SLICE_K 32
+#endif
+constexpr int SLICE_K = RNB_SLICE_K;      // K extent of one ring stage: 32, or 16 (twice as many stages of half the size)
+constexpr int RING_STAGES = 3 * 32 / SLICE_K;
+constexpr int STAGE_BYTES = 512 * SLICE_K;   // one K slice of a 256-row operand (16 KB at K = 32)
 constexpr int CHAIN_THREADS = 320;
 constexpr int EPI_THREADS = 256;
 constexpr int EPI_HALF_COLS = 128;     // accumulator columns owned by one epilogue thread
@@ -115,9 +119,9 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
             // epilogue + one MMA phase before epilogue(st) reads these streams: enough to cover DRAM latency, short
             // enough that the lines are still in L2 (a longer lead measurably doubled DRAM reads).
             chain_prefetch_step(tab, st, tile);
-            const uint32_t bytes = 64u * tab.steps[st].n;                 // 4 chunks x n rows x 16 B
+            const uint32_t bytes = (uint32_t)(2 * SLICE_K) * tab.steps[st].n;   // SLICE_K/8 chunks x n rows x 16 B
             const uint8_t* src = wblob + tab.steps[st].w_off;
-            const int nsl = tab.steps[st].k >> 5;
+            const int nsl = tab.steps[st].k / SLICE_K;
             for (int ks = 0; ks < nsl; ++ks, ++it) {
                 const uint32_t slot = it % RING_STAGES, ph = (it / RING_STAGES) & 1;
                 mbar_wait(&s.empty[slot], ph ^ 1);
@@ -138,7 +142,7 @@ __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& 
         for (int st = 0; st < tab.n_steps; ++st, ++sig) {
             const uint32_t n = tab.steps[st].n;
             const uint32_t idesc = umma_idesc(TILE_M, n, FMT_F16, FMT_F16);
-            const int nsl = tab.steps[st].k >> 5;
+            const int nsl = tab.steps[st].k / SLICE_K;
             mbar_wait(s.a_ready, sig & 1);
             tc_fence_after();
             for (int ks = 0; ks < nsl; ++ks, ++it) {
@@ -146,8 +150,8 @@ __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& 
                 mbar_wait(&s.full[slot], ph);
                 tc_fence_after();
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const uint64_t ad = umma_desc(a_base + (uint32_t)(ks * 2 + j) * (2 * TILE_M * 16), TILE_M * 16, 128);
+                for (int j = 0; j < SLICE_K / 16; ++j) {
+                    const uint64_t ad = umma_desc(a_base + (uint32_t)(ks * (SLICE_K / 16) + j) * (2 * TILE_M * 16), TILE_M * 16, 128);
                     const uint64_t bd = umma_desc(ring_base + slot * STAGE_BYTES + (uint32_t)j * (2 * n * 16), n * 16, 128);
                     umma_f16(tmem, ad, bd, idesc, ((ks | j) != 0) || tab.steps[st].accumulate);
                 }

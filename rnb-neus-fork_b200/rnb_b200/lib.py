@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librnb_b200.so")
+LIB_PATH = os.environ.get("RNB_B200_LIB") or os.path.join(_HERE, "librnb_b200.so")   # override: A/B builds of the same ABI
 
 
 class Points(C.Structure):
