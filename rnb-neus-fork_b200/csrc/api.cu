@@ -167,12 +167,18 @@ static void table_forward(ChainTable& t) {           // layers 0..7
     for (int l = 1; l < 8; ++l) add_step(t, sdfw_fwd(l), 256, 256);
 }
 static int n_tiles(int64_t n) { return (int)((n + TILE_M - 1) / TILE_M); }
+#ifdef RNB_TRACE
+static unsigned long long* g_trace = nullptr;   // device buffer [4 roles][4096][4] of clock64() stamps, CTA 0
+#endif
 }  // namespace rnb
 
 using namespace rnb;
 
 extern "C" {
 
+#ifdef RNB_TRACE
+__attribute__((visibility("default"))) void rnb_trace_set(void* p) { g_trace = (unsigned long long*)p; }
+#endif
 const char* rnb_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 int rnb_version(void) { return 100; }
 size_t rnb_sdf_wblob_bytes(void) { return SDFW_BYTES; }
@@ -191,6 +197,9 @@ int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float* aux, fl
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
     table_forward(P.tab);
+#ifdef RNB_TRACE
+    P.tab.trace = g_trace;
+#endif
     P.out = out;
     P.out_scale = out_scale;
     return (int)profiled(T_SDF_FWD, (cudaStream_t)stream, [&] { return launch_sdf_fwd(P, sm_count(), (cudaStream_t)stream); });
@@ -204,6 +213,9 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
     table_forward(P.tab);
+#ifdef RNB_TRACE
+    P.tab.trace = g_trace;
+#endif
     add_step(P.tab, SDFW_F8, 256, 256);
     {
         const size_t SS = rnb_stream_bytes(pts->n_pts, 256);
@@ -249,6 +261,9 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
         static const int bwd_pf = getenv("RNB_BWD_PF") ? atoi(getenv("RNB_BWD_PF")) : 0;
         static const int bwd_tpf = getenv("RNB_BWD_TPF") ? atoi(getenv("RNB_BWD_TPF")) : 3;
         P.thread_prefetch = bwd_tpf;
+#ifdef RNB_TRACE
+        P.tab.trace = g_trace;
+#endif
         // 25 KB/point of streams flow through L2 in this kernel: pin the 2 MB of weights (5.47 -> 5.24 ms); the other
         // chain kernels measured 3-5 % slower with the hinted copy, so they keep the plain one
         P.tab.weights_evict_last = 1;

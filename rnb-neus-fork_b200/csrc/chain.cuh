@@ -43,7 +43,13 @@ struct ChainTable {
     int n_steps;
     int weights_evict_last;   // load the weight slices with an L2 evict-last policy (pays off only under heavy stream traffic)
     ChainStep steps[MAX_STEPS];
+    unsigned long long* trace;   // RNB_TRACE builds only: CTA 0 records clock64() timestamps (see profiles/_trace_chain.py)
 };
+#ifdef RNB_TRACE
+#define RNB_TR(role, idx, k, cond) do { if ((cond) && tab_trace && blockIdx.x == 0 && (idx) < 4096) tab_trace[((role) * 4096 + (idx)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define RNB_TR(role, idx, k, cond) do { } while (0)
+#endif
 
 struct ChainSmem {
     uint8_t* sA;
@@ -111,6 +117,7 @@ __device__ __forceinline__ void chain_prefetch_step(const ChainTable& tab, int s
 
 __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTable& tab, const uint8_t* wblob, int n_my_tiles) {
     uint32_t it = 0;
+    unsigned long long* tab_trace = tab.trace; (void)tab_trace;
     const uint64_t keep = l2_policy_evict_last();
     for (int t = 0; t < n_my_tiles; ++t) {
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
@@ -124,11 +131,60 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
             const int nsl = tab.steps[st].k / SLICE_K;
             for (int ks = 0; ks < nsl; ++ks, ++it) {
                 const uint32_t slot = it % RING_STAGES, ph = (it / RING_STAGES) & 1;
+                RNB_TR(0, it, 0, true);
                 mbar_wait(&s.empty[slot], ph ^ 1);
+                RNB_TR(0, it, 1, true);
                 mbar_expect_tx(&s.full[slot], bytes);
                 if (tab.weights_evict_last) bulk_g2s_hint(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot], keep);
                 else bulk_g2s(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot]);
+                RNB_TR(0, it, 2, true);
             }
+        }
+    }
+}
+
+// warp 1, ALL lanes (convergent): the waits are warp-wide, one elected lane issues.  Compared with running the whole
+// loop inside `if (lane == 0)`, loop counters and descriptors stay in uniform registers and each tcgen05 instruction
+// needs no per-instruction elect loop; ring slot / phase are carried incrementally (no division by RING_STAGES) and
+// the operand descriptors are formed by adding to per-step bases (address field = bytes >> 4; smem addresses stay
+// below 2^18, so the adds never carry out of the 14-bit field).  The issue loop, not the weight ring, paced the MMA
+// phase before (profiles/r01_notes.md: clock64 trace of one CTA).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void chain_mma_warp(const ChainSmem& s, const ChainTable& tab, uint32_t tmem, int n_my_tiles) {
+    uint32_t slot = 0, ph = 0, sig = 0;
+    const uint64_t a_desc0 = umma_desc(smem_u32(s.sA), TILE_M * 16, 128);
+    const uint32_t ring_base = smem_u32(s.ring);
+    for (int t = 0; t < n_my_tiles; ++t) {
+        for (int st = 0; st < tab.n_steps; ++st, ++sig) {
+            const uint32_t n = tab.steps[st].n;
+            const uint32_t idesc = umma_idesc(TILE_M, n, FMT_F16, FMT_F16);
+            const int nsl = tab.steps[st].k / SLICE_K;
+            const uint64_t b_desc0 = umma_desc(ring_base, n * 16, 128);
+            const uint32_t b_slab = (2 * n * 16) >> 4;          // one K=16 slab of the stage, in descriptor units
+            const uint32_t acc0 = tab.steps[st].accumulate;
+            mbar_wait(s.a_ready, sig & 1);
+            tc_fence_after();
+            for (int ks = 0; ks < nsl; ++ks) {
+                mbar_wait(&s.full[slot], ph);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < SLICE_K / 16; ++j) {
+                        const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(ks * (SLICE_K / 16) + j) * ((2 * TILE_M * 16) >> 4));
+                        const uint64_t bd = b_desc0 + (uint64_t)(slot * (STAGE_BYTES >> 4) + (uint32_t)j * b_slab);
+                        umma_f16(tmem, ad, bd, idesc, ((ks | j) != 0) || acc0);
+                    }
+                    umma_commit(&s.empty[slot]);
+                }
+                __syncwarp();
+                if (++slot == RING_STAGES) { slot = 0; ph ^= 1; }
+            }
+            if (elect_one()) umma_commit(s.acc_full);
+            __syncwarp();
         }
     }
 }
@@ -136,6 +192,7 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
 // warp 1, one lane
 __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& tab, uint32_t tmem, int n_my_tiles) {
     uint32_t it = 0, sig = 0;
+    unsigned long long* tab_trace = tab.trace; (void)tab_trace;
     const uint32_t a_base = smem_u32(s.sA);
     const uint32_t ring_base = smem_u32(s.ring);
     for (int t = 0; t < n_my_tiles; ++t) {
@@ -143,11 +200,15 @@ __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& 
             const uint32_t n = tab.steps[st].n;
             const uint32_t idesc = umma_idesc(TILE_M, n, FMT_F16, FMT_F16);
             const int nsl = tab.steps[st].k / SLICE_K;
+            RNB_TR(2, sig, 0, true);
             mbar_wait(s.a_ready, sig & 1);
+            RNB_TR(2, sig, 1, true);
             tc_fence_after();
             for (int ks = 0; ks < nsl; ++ks, ++it) {
                 const uint32_t slot = it % RING_STAGES, ph = (it / RING_STAGES) & 1;
+                RNB_TR(1, it, 0, true);
                 mbar_wait(&s.full[slot], ph);
+                RNB_TR(1, it, 1, true);
                 tc_fence_after();
 #pragma unroll
                 for (int j = 0; j < SLICE_K / 16; ++j) {
@@ -156,8 +217,10 @@ __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& 
                     umma_f16(tmem, ad, bd, idesc, ((ks | j) != 0) || tab.steps[st].accumulate);
                 }
                 umma_commit(&s.empty[slot]);
+                RNB_TR(1, it, 2, true);
             }
             umma_commit(s.acc_full);
+            RNB_TR(2, sig, 2, true);
         }
     }
 }
@@ -184,9 +247,13 @@ struct Epi {
         half = (warp - 2) >> 2;
         col0 = half * EPI_HALF_COLS;
         acc_cnt = 0;
+        tab_trace = nullptr;
     }
+    unsigned long long* tab_trace;
     __device__ __forceinline__ void wait_acc() {
+        RNB_TR(3, acc_cnt, 0, threadIdx.x == 64);
         mbar_wait(acc_full, acc_cnt & 1);
+        RNB_TR(3, acc_cnt, 1, threadIdx.x == 64);
         ++acc_cnt;
         tc_fence_after();
     }
@@ -194,6 +261,7 @@ struct Epi {
     __device__ __forceinline__ void signal() {
         tc_fence_before();
         fence_proxy_async();
+        RNB_TR(3, acc_cnt, 2, threadIdx.x == 64);
         mbar_arrive(a_ready);
     }
     // rendezvous of the 256 epilogue threads (named barrier 1; warps 0/1 never join)
@@ -319,6 +387,50 @@ __device__ __forceinline__ float softplus100(float z) {
     const float q = ex2_approx(-144.26950408889634f * fabsf(z));
     return fmaf(q, softplus100_corr(q), fmaxf(z, 0.f));
 }
+// ---- packed fp32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 lanes per instruction).  The epilogues are bound by
+// issue slots, not by the FMA pipe, so doing the bias add, the exponent scaling and the log1p polynomial on pairs of
+// columns removes ~7 of 19 instructions per pair with bit-identical results (same operations, same rounding).
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
+// softplus100 of two columns; same arithmetic as softplus100() lane by lane
+__device__ __forceinline__ float2 softplus100_x2(float2 z) {
+    const float2 y = f2_mul(z, f2_splat(144.26950408889634f));
+    float2 q;
+    q.x = ex2_approx(-fabsf(y.x));
+    q.y = ex2_approx(-fabsf(y.y));
+    float2 p = f2_fma(q, f2_splat(0.04106372e-2f), f2_splat(-0.15602615e-2f));
+    p = f2_fma(q, p, f2_splat(0.30467027e-2f));
+    p = f2_fma(q, p, f2_splat(-0.49636758e-2f));
+    p = f2_fma(q, p, f2_splat(0.99988786e-2f));
+    return f2_fma(q, p, make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f)));
+}
+
 // softplus'(z) recovered from a = softplus(z):  a = log(1 + e^{100 z}) / 100  =>  sigmoid(100 z) = 1 - e^{-100 a}.
 // Lets the backward kernels read the activation stream they need anyway instead of a separate s stream.
 __device__ __forceinline__ float sig_from_a(float a) { return 1.f - ex2_approx(-144.26950408889634f * a); }

@@ -37,13 +37,17 @@ __device__ __forceinline__ void fwd_layer_plain(const Epi& ep, const float* bias
     ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            float bb[8], a[8];
+            float bb[8];
             load_bias8(bias + c0 + q * 8, bb);
+            uint32_t hh[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]);
-            uint4 h;
-            h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
-            ep.st_a((c0 >> 3) + q, h);
+            for (int j = 0; j < 4; ++j) {
+                const float2 z = f2_add(make_float2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1])),
+                                        make_float2(bb[2 * j], bb[2 * j + 1]));
+                const float2 a = softplus100_x2(z);
+                hh[j] = pack_h2(a.x, a.y);
+            }
+            ep.st_a((c0 >> 3) + q, make_uint4(hh[0], hh[1], hh[2], hh[3]));
         }
     });
 }
@@ -57,7 +61,13 @@ __device__ __forceinline__ float fwd_layer_last(const Epi& ep, const float* bias
             load_bias8(bias + c0 + q * 8, bb);
             load_bias8(w8row + c0 + q * 8, ww);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc = fmaf(softplus100(__uint_as_float(v[q * 8 + j]) + bb[j]), ww[j], acc);
+            for (int j = 0; j < 4; ++j) {
+                const float2 z = f2_add(make_float2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1])),
+                                        make_float2(bb[2 * j], bb[2 * j + 1]));
+                const float2 a = softplus100_x2(z);
+                acc = fmaf(a.x, ww[2 * j], acc);
+                acc = fmaf(a.y, ww[2 * j + 1], acc);
+            }
         }
     });
     return acc;
@@ -119,10 +129,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_kernel(const __grid_
     if (warp == 0) {
         if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
     } else if (warp == 1) {
+#ifdef RNB_MMA_V1
         if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
+#else
+        chain_mma_warp(s, P.tab, tmem, n_my);
+#endif
     } else {
         Epi ep;
         ep.init(s, tmem);
+#ifdef RNB_TRACE
+        ep.tab_trace = P.tab.trace;
+#endif
         const float* bias = P.aux;
         const float* w8row = P.aux + AUX_W8ROW;
         const float b8 = __ldg(P.aux + AUX_B8_0);
@@ -163,10 +180,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
     if (warp == 0) {
         if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
     } else if (warp == 1) {
+#ifdef RNB_MMA_V1
         if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
+#else
+        chain_mma_warp(s, P.tab, tmem, n_my);
+#endif
     } else {
         Epi ep;
         ep.init(s, tmem);
+#ifdef RNB_TRACE
+        ep.tab_trace = P.tab.trace;
+#endif
         const float* bias = P.aux;
         const float* w8row = P.aux + AUX_W8ROW;
         const size_t SS = P.stream_stride;
@@ -382,10 +406,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
     if (warp == 0) {
         if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
     } else if (warp == 1) {
+#ifdef RNB_MMA_V1
         if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
+#else
+        chain_mma_warp(s, P.tab, tmem, n_my);
+#endif
     } else {
         Epi ep;
         ep.init(s, tmem);
+#ifdef RNB_TRACE
+        ep.tab_trace = P.tab.trace;
+#endif
         const float* w8row = P.aux + AUX_W8ROW;
         const size_t SS = P.stream_stride;
         const float scale = cot_scale_from_max(__ldg(P.cot_absmax));
