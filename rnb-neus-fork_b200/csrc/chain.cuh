@@ -225,6 +225,92 @@ __device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& 
     }
 }
 
+// ---- activations (fp32, MUFU based)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus(beta=100): a = log(1+exp(100 z))/100  (reference models/fields.py:80).  The ATen threshold branch
+// (100 z > 20 -> a = z) differs from this closed form by < 2.1e-11, far below fp32 resolution of a.
+//   a = max(z, 0) + log1p(q) / 100,   q = exp(-100 |z|) in (0, 1]
+// One MUFU (ex2) per element: log1p(q) = q * P4(q) with a degree-4 minimax polynomial on the FMA pipe (relative error
+// 1.2e-4, i.e. < 8.1e-7 absolute on a -- below half an fp16 ulp of every activation the correction matters for).
+// The XU pipe (16 lanes/clk/SM) is what bounds the forward layers; a second MUFU (lg2) would double that floor.
+__device__ __forceinline__ float softplus100_corr(float q) {
+    // coefficients of log1p(q)/q, pre-divided by 100
+    float p = fmaf(q, 0.04106372e-2f, -0.15602615e-2f);
+    p = fmaf(q, p, 0.30467027e-2f);
+    p = fmaf(q, p, -0.49636758e-2f);
+    p = fmaf(q, p, 0.99988786e-2f);
+    return p;
+}
+__device__ __forceinline__ float softplus100(float z) {
+    const float q = ex2_approx(-144.26950408889634f * fabsf(z));
+    return fmaf(q, softplus100_corr(q), fmaxf(z, 0.f));
+}
+// ---- packed fp32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 lanes per instruction).  The epilogues are bound by
+// issue slots, not by the FMA pipe, so doing the bias add, the exponent scaling and the log1p polynomial on pairs of
+// columns removes ~7 of 19 instructions per pair with bit-identical results (same operations, same rounding).
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
+// softplus100 of two columns; same arithmetic as softplus100() lane by lane
+__device__ __forceinline__ float2 softplus100_x2(float2 z) {
+    const float2 y = f2_mul(z, f2_splat(144.26950408889634f));
+    float2 q;
+    q.x = ex2_approx(-fabsf(y.x));
+    q.y = ex2_approx(-fabsf(y.y));
+    float2 p = f2_fma(q, f2_splat(0.04106372e-2f), f2_splat(-0.15602615e-2f));
+    p = f2_fma(q, p, f2_splat(0.30467027e-2f));
+    p = f2_fma(q, p, f2_splat(-0.49636758e-2f));
+    p = f2_fma(q, p, f2_splat(0.99988786e-2f));
+    return f2_fma(q, p, make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f)));
+}
+
+// softplus'(z) recovered from a = softplus(z):  a = log(1 + e^{100 z}) / 100  =>  sigmoid(100 z) = 1 - e^{-100 a}.
+// Lets the backward kernels read the activation stream they need anyway instead of a separate s stream.
+__device__ __forceinline__ float sig_from_a(float a) { return 1.f - ex2_approx(-144.26950408889634f * a); }
+// (1 - exp(-100 a)) * u on two columns: same operations and rounding as sig_from_a(a) * u lane by lane
+__device__ __forceinline__ float2 sigmul_x2(float2 a, float2 u) {
+    const float2 y = f2_mul(a, f2_splat(144.26950408889634f));
+    float2 e;
+    e.x = ex2_approx(-y.x);
+    e.y = ex2_approx(-y.y);
+    return f2_mul(f2_fma(e, f2_splat(-1.f), f2_splat(1.f)), u);
+}
+
+
 // per-thread epilogue context (warps 2..9)
 struct Epi {
     uint8_t* sA;
@@ -319,10 +405,9 @@ struct Epi {
             float z[16];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                z[4 * k] = __uint_as_float(v[4 * k]) + nb[k].x;
-                z[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + nb[k].y;
-                z[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + nb[k].z;
-                z[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + nb[k].w;
+                const float2 z0 = f2_add(make_float2(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1])), make_float2(nb[k].x, nb[k].y));
+                const float2 z1 = f2_add(make_float2(__uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])), make_float2(nb[k].z, nb[k].w));
+                z[4 * k] = z0.x; z[4 * k + 1] = z0.y; z[4 * k + 2] = z1.x; z[4 * k + 3] = z1.y;
             }
             if (c0 + 16 < col0 + EPI_HALF_COLS) {
                 const float4* np = reinterpret_cast<const float4*>(bias + c0 + 16);
@@ -357,82 +442,5 @@ __device__ __forceinline__ void prefetch_stream_chunks(const uint8_t* base, int6
         for (int k = 0; k < n_chunks; ++k) prefetch_l2(base + stream_off(p, chunk0 + k, 32));
     }
 }
-
-// ---- activations (fp32, MUFU based)
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// softplus(beta=100): a = log(1+exp(100 z))/100  (reference models/fields.py:80).  The ATen threshold branch
-// (100 z > 20 -> a = z) differs from this closed form by < 2.1e-11, far below fp32 resolution of a.
-//   a = max(z, 0) + log1p(q) / 100,   q = exp(-100 |z|) in (0, 1]
-// One MUFU (ex2) per element: log1p(q) = q * P4(q) with a degree-4 minimax polynomial on the FMA pipe (relative error
-// 1.2e-4, i.e. < 8.1e-7 absolute on a -- below half an fp16 ulp of every activation the correction matters for).
-// The XU pipe (16 lanes/clk/SM) is what bounds the forward layers; a second MUFU (lg2) would double that floor.
-__device__ __forceinline__ float softplus100_corr(float q) {
-    // coefficients of log1p(q)/q, pre-divided by 100
-    float p = fmaf(q, 0.04106372e-2f, -0.15602615e-2f);
-    p = fmaf(q, p, 0.30467027e-2f);
-    p = fmaf(q, p, -0.49636758e-2f);
-    p = fmaf(q, p, 0.99988786e-2f);
-    return p;
-}
-__device__ __forceinline__ float softplus100(float z) {
-    const float q = ex2_approx(-144.26950408889634f * fabsf(z));
-    return fmaf(q, softplus100_corr(q), fmaxf(z, 0.f));
-}
-// ---- packed fp32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 lanes per instruction).  The epilogues are bound by
-// issue slots, not by the FMA pipe, so doing the bias add, the exponent scaling and the log1p polynomial on pairs of
-// columns removes ~7 of 19 instructions per pair with bit-identical results (same operations, same rounding).
-__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-        "mov.b64 {%0, %1}, rd;}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
-}
-__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "mul.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
-// softplus100 of two columns; same arithmetic as softplus100() lane by lane
-__device__ __forceinline__ float2 softplus100_x2(float2 z) {
-    const float2 y = f2_mul(z, f2_splat(144.26950408889634f));
-    float2 q;
-    q.x = ex2_approx(-fabsf(y.x));
-    q.y = ex2_approx(-fabsf(y.y));
-    float2 p = f2_fma(q, f2_splat(0.04106372e-2f), f2_splat(-0.15602615e-2f));
-    p = f2_fma(q, p, f2_splat(0.30467027e-2f));
-    p = f2_fma(q, p, f2_splat(-0.49636758e-2f));
-    p = f2_fma(q, p, f2_splat(0.99988786e-2f));
-    return f2_fma(q, p, make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f)));
-}
-
-// softplus'(z) recovered from a = softplus(z):  a = log(1 + e^{100 z}) / 100  =>  sigmoid(100 z) = 1 - e^{-100 a}.
-// Lets the backward kernels read the activation stream they need anyway instead of a separate s stream.
-__device__ __forceinline__ float sig_from_a(float a) { return 1.f - ex2_approx(-144.26950408889634f * a); }
 
 }  // namespace rnb

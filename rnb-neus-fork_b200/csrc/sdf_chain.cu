@@ -216,9 +216,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
                         float a[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            a[j] = softplus100(z[q * 8 + j]);
-                            if (l == 7) sdf = fmaf(a[j], ww[j], sdf);
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 aa = softplus100_x2(make_float2(z[q * 8 + 2 * j], z[q * 8 + 2 * j + 1]));
+                            a[2 * j] = aa.x;
+                            a[2 * j + 1] = aa.y;
+                            if (l == 7) {
+                                sdf = fmaf(aa.x, ww[2 * j], sdf);
+                                sdf = fmaf(aa.y, ww[2 * j + 1], sdf);
+                            }
                         }
                         uint4 ha;
                         ha.x = pack_h2(a[0], a[1]); ha.y = pack_h2(a[2], a[3]); ha.z = pack_h2(a[4], a[5]); ha.w = pack_h2(a[6], a[7]);
@@ -257,10 +262,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         const uint4 ha7 = ep.ld_a(ch);
                         const float2 s0 = unpack_h2(ha7.x), s1 = unpack_h2(ha7.y), s2 = unpack_h2(ha7.z), s3 = unpack_h2(ha7.w);
                         uint4 hw;
-                        hw.x = pack_h2(sig_from_a(s0.x) * ww[0], sig_from_a(s0.y) * ww[1]);
-                        hw.y = pack_h2(sig_from_a(s1.x) * ww[2], sig_from_a(s1.y) * ww[3]);
-                        hw.z = pack_h2(sig_from_a(s2.x) * ww[4], sig_from_a(s2.y) * ww[5]);
-                        hw.w = pack_h2(sig_from_a(s3.x) * ww[6], sig_from_a(s3.y) * ww[7]);
+                        const float2 w0 = sigmul_x2(s0, make_float2(ww[0], ww[1])), w1 = sigmul_x2(s1, make_float2(ww[2], ww[3]));
+                        const float2 w2 = sigmul_x2(s2, make_float2(ww[4], ww[5])), w3 = sigmul_x2(s3, make_float2(ww[6], ww[7]));
+                        hw.x = pack_h2(w0.x, w0.y); hw.y = pack_h2(w1.x, w1.y); hw.z = pack_h2(w2.x, w2.y); hw.w = pack_h2(w3.x, w3.y);
                         ep.st_a(ch, hw);
                         if (P.st_w) st_stream(st_w7, p, ch, 32, hw);
                     }
@@ -306,10 +310,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
 #pragma unroll
                         for (int j = 0; j < 8; ++j) u[j] = __uint_as_float(v[q * 8 + j]);
                         uint4 hw;
-                        hw.x = pack_h2(sig_from_a(s0.x) * u[0], sig_from_a(s0.y) * u[1]);
-                        hw.y = pack_h2(sig_from_a(s1.x) * u[2], sig_from_a(s1.y) * u[3]);
-                        hw.z = pack_h2(sig_from_a(s2.x) * u[4], sig_from_a(s2.y) * u[5]);
-                        hw.w = pack_h2(sig_from_a(s3.x) * u[6], sig_from_a(s3.y) * u[7]);
+                        const float2 w0 = sigmul_x2(s0, make_float2(u[0], u[1])), w1 = sigmul_x2(s1, make_float2(u[2], u[3]));
+                        const float2 w2 = sigmul_x2(s2, make_float2(u[4], u[5])), w3 = sigmul_x2(s3, make_float2(u[6], u[7]));
+                        hw.x = pack_h2(w0.x, w0.y); hw.y = pack_h2(w1.x, w1.y); hw.z = pack_h2(w2.x, w2.y); hw.w = pack_h2(w3.x, w3.y);
                         ep.st_a(ch, hw);
                         if (P.st_w) st_stream(st_wp, p, ch, 32, hw);
                     }
@@ -396,6 +399,19 @@ __device__ __forceinline__ float zbar_elem(float a, float w, float u, float abar
     const float r = s > 1e-6f ? rcp_approx(s) : 0.f;
     return fmaf(s, abar, 100.f * e * w * (u * r));
 }
+// two columns at once (packed fp32; same operations and rounding lane by lane)
+__device__ __forceinline__ float2 zbar_x2(float2 a, float2 w, float2 u, float2 abar) {
+    const float2 y = f2_mul(a, f2_splat(144.26950408889634f));
+    float2 e;
+    e.x = ex2_approx(-y.x);
+    e.y = ex2_approx(-y.y);
+    const float2 s = f2_fma(e, f2_splat(-1.f), f2_splat(1.f));
+    float2 r;
+    r.x = s.x > 1e-6f ? rcp_approx(s.x) : 0.f;
+    r.y = s.y > 1e-6f ? rcp_approx(s.y) : 0.f;
+    const float2 t = f2_mul(f2_mul(f2_mul(e, f2_splat(100.f)), w), f2_mul(u, r));
+    return f2_fma(s, abar, t);
+}
 
 __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __grid_constant__ SdfBwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -476,8 +492,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                             const float2 av = unpack_h2(hsa[j]);
                             const float wb0 = __uint_as_float(v[q * 8 + 2 * j]), wb1 = __uint_as_float(v[q * 8 + 2 * j + 1]);
                             // s wbar = wbar - exp(-100 a) wbar
-                            ub[j] = pack_h2_sat(fmaf(-ex2_approx(-144.26950408889634f * av.x), wb0, wb0),
-                                                fmaf(-ex2_approx(-144.26950408889634f * av.y), wb1, wb1));
+                            const float2 y = f2_mul(av, f2_splat(144.26950408889634f));
+                            const float2 wb = make_float2(wb0, wb1);
+                            const float2 uu2 = f2_fma(make_float2(ex2_approx(-y.x), ex2_approx(-y.y)), f2_mul(wb, f2_splat(-1.f)), wb);
+                            ub[j] = pack_h2_sat(uu2.x, uu2.y);
                         }
                         const uint4 uu = make_uint4(ub[0], ub[1], ub[2], ub[3]);
                         st_stream(st_un, p, ch, 32, uu);
@@ -561,7 +579,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_bwd_data_kernel(const __
                                 a0 = fmaf(dsdf, ww[2 * j], a0);
                                 a1 = fmaf(dsdf, ww[2 * j + 1], a1);
                             }
-                            zb[j] = pack_h2_sat(zbar_elem(av.x, wv.x, uv.x, a0), zbar_elem(av.y, wv.y, uv.y, a1));
+                            const float2 zz = zbar_x2(av, wv, uv, make_float2(a0, a1));
+                            zb[j] = pack_h2_sat(zz.x, zz.y);
                         }
                         const uint4 uz = make_uint4(zb[0], zb[1], zb[2], zb[3]);
                         st_stream(st_zb, p, ch, 32, uz);
