@@ -46,22 +46,18 @@ t = trace.cpu().numpy().reshape(4, 4096, 4)
 n_steps = {"k1": 8, "k2": 17, "k3a": 16}[which]
 t0 = t[2, 0, 1]
 np.save(os.path.join(ROOT, "gpurun_out", f"trace_{which}.npy"), t)
-# steady state: tiles 2.. of CTA 0
-print(f"{which}: per-step timeline of CTA 0 (cycles), tile 3")
-for s in range(3 * n_steps, 4 * n_steps):
-    a_wait0, a_seen, acc_commit = t[2, s, :3]
-    e_wait0, e_seen, e_sig = t[3, s + 1 if which != "k1" else s, :3] if False else t[3, s, :3]
-    print(f"step {s % n_steps:2d}: mma waits a_ready {a_seen - a_wait0:6d} | mma issue phase {acc_commit - a_seen:6d} | "
-          f"epi waits acc {e_seen - e_wait0:6d} (acc seen {e_seen - a_seen:6d} after a_ready) | epi work -> signal {e_sig - e_seen:6d}")
-# per-slice details of one step
-it0 = None
-sl = t[1]
-print("per-slice (MMA thread): wait_full, then issue; producer: wait_empty, issue  -- relative to a_ready of that step")
-step = 3 * n_steps + min(2, n_steps - 1)
-a_seen = t[2, step, 1]
-# find slices whose full_seen lies between a_seen and acc commit
-lo, hi = a_seen, t[2, step, 2]
-for i in range(4096):
-    if sl[i, 1] >= lo and sl[i, 2] <= hi + 10 and sl[i, 1] > 0:
-        p = t[0, i]
-        print(f"  slice {i}: producer wait_empty {p[0] - lo:7d}..{p[1] - lo:7d} issued {p[2] - lo:7d} | mma wait_full {sl[i, 0] - lo:6d}..{sl[i, 1] - lo:6d} issued {sl[i, 2] - lo:6d}")
+# averages over the tiles of CTA 0 (first two and last skipped), per step index, seen by epilogue thread 64
+t = t.astype(np.int64)
+n_tiles = int((t[3, :, 1] > 0).sum()) // n_steps
+print(f"{which}: CTA 0, {n_tiles} tiles; mean cycles per step")
+print("step | epilogue waits for the accumulator (= MMA phase as the epilogue sees it) | epilogue work (acc seen -> signal)")
+tot_w = tot_e = 0.0
+for st in range(n_steps):
+    idx = np.array([tile * n_steps + st for tile in range(2, n_tiles - 1)])
+    wait = (t[3, idx, 1] - t[3, idx, 0]).mean()
+    work = (t[3, idx + 1, 2] - t[3, idx, 1]).mean() if st + 1 < n_steps else float("nan")
+    tot_w += wait
+    tot_e += 0.0 if work != work else work
+    print(f"{st:4d} | {wait:8.0f} | {work:8.0f}")
+span = (t[3, (n_tiles - 2) * n_steps, 1] - t[3, 2 * n_steps, 1]) / (n_tiles - 4)
+print(f"sum of waits {tot_w:.0f}, sum of work {tot_e:.0f} (last step's work not recorded), cycles per tile {span:.0f}")
