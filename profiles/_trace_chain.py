@@ -32,8 +32,16 @@ d_sdf = torch.randn(n, device="cuda") * 1e-4
 d_grad = torch.randn(n, 3, device="cuda") * 1e-5
 scratch = torch.empty(lib.rnb_sdf_bwd_scratch_bytes(n), dtype=torch.uint8, device="cuda")
 K.sdf_fwd_grad(pk, pts, st)
+from rnb_b200 import albedo as A  # noqa: E402
+sdf_out, grad_out = K.sdf_fwd_grad(pk, pts, st)[:2]
+with torch.no_grad():
+    col_flat = [t.detach().contiguous() for wb in col.effective_weights() for t in wb]
+actx = A.forward(col_flat, pts, grad_out.contiguous(), st)
+d_alb = torch.randn(n, 3, device="cuda") * 1e-4
 fn = {"k1": lambda: K.sdf_fwd(pk, pts), "k2": lambda: K.sdf_fwd_grad(pk, pts, st),
-      "k3a": lambda: K.sdf_bwd(pk, pts, st, d_sdf, d_grad, None, scratch)}[which]
+      "k3a": lambda: K.sdf_bwd(pk, pts, st, d_sdf, d_grad, None, scratch),
+      "alb_fwd": lambda: A.forward(col_flat, pts, grad_out.contiguous(), st),
+      "alb_bwd": lambda: A.backward(actx, d_alb)}[which]
 for _ in range(2):
     fn()
 torch.cuda.synchronize()
@@ -43,7 +51,7 @@ fn()
 torch.cuda.synchronize()
 raw.rnb_trace_set(None)
 t = trace.cpu().numpy().reshape(4, 4096, 4)
-n_steps = {"k1": 8, "k2": 17, "k3a": 16}[which]
+n_steps = {"k1": 8, "k2": 17, "k3a": 16, "alb_fwd": 3, "alb_bwd": 3}[which]
 t0 = t[2, 0, 1]
 np.save(os.path.join(ROOT, "gpurun_out", f"trace_{which}.npy"), t)
 # averages over the tiles of CTA 0 (first two and last skipped), per step index, seen by epilogue thread 64

@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
     } else {
         Epi ep;
         ep.init(s, tmem);
+#ifdef RNB_TRACE
+        ep.tab_trace = P.tab.trace;
+#endif
         const float* b0 = P.aux + ALBX_B0;
         const float* b1 = P.aux + ALBX_B1;
         const float* w2 = P.aux + ALBX_W2;
@@ -148,6 +151,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
     } else {
         Epi ep;
         ep.init(s, tmem);
+#ifdef RNB_TRACE
+        ep.tab_trace = P.tab.trace;
+#endif
         const float* w2 = P.aux + ALBX_W2;
         const float scale = cot_scale_from_max(__ldg(P.cot_absmax));
         const float inv_scale = 1.f / scale;

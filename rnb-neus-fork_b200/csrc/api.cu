@@ -458,6 +458,9 @@ int rnb_albedo_fwd(const rnb_points_t* pts, const float* normals, const void* st
     P.n_tiles = n_tiles(pts->n_pts);
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
+#ifdef RNB_TRACE
+    P.tab.trace = g_trace;
+#endif
     add_step(P.tab, ALBW_F0A, 256, 256);
     add_step(P.tab, ALBW_F0B, 256, 64, 1);
     add_step(P.tab, ALBW_F1, 256, 256);
@@ -490,6 +493,9 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     P.n_tiles = n_tiles(n);
     P.wblob = (const uint8_t*)wblob;
     P.aux = aux;
+#ifdef RNB_TRACE
+    P.tab.trace = g_trace;
+#endif
     add_step(P.tab, ALBW_T1, 256, 256);
     add_step(P.tab, ALBW_T0A, 256, 256);
     add_step(P.tab, ALBW_T0B, 64, 256);

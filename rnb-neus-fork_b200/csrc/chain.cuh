@@ -436,6 +436,11 @@ __device__ __forceinline__ uint4 ld_stream(const uint8_t* base, int64_t p, int c
 // completion to wait for).  A warp's 32 rows x 16 B of one chunk are 512 contiguous bytes = four 128-byte lines:
 // one lane in eight issues the hint.  The epilogue loads then hit L2 instead of waiting a DRAM round trip per chunk.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 128 consecutive floats (4 lines) towards L1 ahead of un-pipelined __ldg reads
+__device__ __forceinline__ void prefetch_l1_row128(const float* p) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32 * k));
+}
 __device__ __forceinline__ void prefetch_stream_chunks(const uint8_t* base, int64_t p, int chunk0, int n_chunks) {
     if ((threadIdx.x & 7) == 0) {
 #pragma unroll 4

@@ -212,18 +212,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                 ep.sweep_half_bias(bl, [&](int c0, const float (&z)[16]) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        float ww[8];
-                        if (l == 7) load_bias8(w8row + c0 + q * 8, ww);
                         float a[8];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float2 aa = softplus100_x2(make_float2(z[q * 8 + 2 * j], z[q * 8 + 2 * j + 1]));
                             a[2 * j] = aa.x;
                             a[2 * j + 1] = aa.y;
-                            if (l == 7) {
-                                sdf = fmaf(aa.x, ww[2 * j], sdf);
-                                sdf = fmaf(aa.y, ww[2 * j + 1], sdf);
-                            }
                         }
                         uint4 ha;
                         ha.x = pack_h2(a[0], a[1]); ha.y = pack_h2(a[2], a[3]); ha.z = pack_h2(a[4], a[5]); ha.w = pack_h2(a[6], a[7]);
@@ -262,6 +256,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         const uint4 ha7 = ep.ld_a(ch);
                         const float2 s0 = unpack_h2(ha7.x), s1 = unpack_h2(ha7.y), s2 = unpack_h2(ha7.z), s3 = unpack_h2(ha7.w);
                         uint4 hw;
+                        // sdf = <a_7, W_8[0,:]> + b_8[0]: this half's part, from the operand image of a_7 (fp16, exactly what
+                        // the 256 feature rows of the same layer are computed from) -- a special case inside the layer-7
+                        // sweep cost that step ~6000 cycles per tile (registers), here W_8[0,:] is loaded anyway
+                        sdf = fmaf(s0.x, ww[0], sdf); sdf = fmaf(s0.y, ww[1], sdf); sdf = fmaf(s1.x, ww[2], sdf); sdf = fmaf(s1.y, ww[3], sdf);
+                        sdf = fmaf(s2.x, ww[4], sdf); sdf = fmaf(s2.y, ww[5], sdf); sdf = fmaf(s3.x, ww[6], sdf); sdf = fmaf(s3.y, ww[7], sdf);
                         const float2 w0 = sigmul_x2(s0, make_float2(ww[0], ww[1])), w1 = sigmul_x2(s1, make_float2(ww[2], ww[3]));
                         const float2 w2 = sigmul_x2(s2, make_float2(ww[4], ww[5])), w3 = sigmul_x2(s3, make_float2(ww[6], ww[7]));
                         hw.x = pack_h2(w0.x, w0.y); hw.y = pack_h2(w1.x, w1.y); hw.z = pack_h2(w2.x, w2.y); hw.w = pack_h2(w3.x, w3.y);
