@@ -98,19 +98,26 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
             ep.signal();
             // step 1: h1 = relu(z1 + b1); albedo = sigmoid(W2 h1 + b2)
             ep.wait_acc();
-            float o[3] = {0.f, 0.f, 0.f};
+            // the three output dot products accumulate on column pairs (packed fp32), folded at the end
+            float2 o2[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
             ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     float bb[8], a[8], w[8];
                     load_bias8(b1 + c0 + q * 8, bb);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bb[j], 0.f);
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 z = f2_add(make_float2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1])),
+                                                make_float2(bb[2 * j], bb[2 * j + 1]));
+                        a[2 * j] = fmaxf(z.x, 0.f);
+                        a[2 * j + 1] = fmaxf(z.y, 0.f);
+                    }
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         load_bias8(w2 + k * 256 + c0 + q * 8, w);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[k] = fmaf(a[j], w[j], o[k]);
+                        for (int j = 0; j < 4; ++j)
+                            o2[k] = f2_fma(make_float2(a[2 * j], a[2 * j + 1]), make_float2(w[2 * j], w[2 * j + 1]), o2[k]);
                     }
                     uint4 h;
                     h.x = pack_h2(a[0], a[1]); h.y = pack_h2(a[2], a[3]); h.z = pack_h2(a[4], a[5]); h.w = pack_h2(a[6], a[7]);
@@ -118,6 +125,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
                 }
             });
             // the two column halves of a row combine their partial dot products through the dead A buffer
+            const float o[3] = {o2[0].x + o2[0].y, o2[1].x + o2[1].y, o2[2].x + o2[2].y};
             if (ep.half == 1) {
                 float* xc = ep.xchg();
                 xc[0] = o[0]; xc[1] = o[1]; xc[2] = o[2];
@@ -189,11 +197,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 hv = unpack_h2(ha[j]);
-                    float d0 = (dz2[0] * w0[2 * j] + dz2[1] * w1[2 * j] + dz2[2] * w2r[2 * j]) * scale;
-                    float d1 = (dz2[0] * w0[2 * j + 1] + dz2[1] * w1[2 * j + 1] + dz2[2] * w2r[2 * j + 1]) * scale;
-                    if (!(hv.x > 0.f)) d0 = 0.f;
-                    if (!(hv.y > 0.f)) d1 = 0.f;
-                    o[j] = pack_h2_sat(d0, d1);
+                    float2 d = f2_mul(f2_splat(dz2[0]), make_float2(w0[2 * j], w0[2 * j + 1]));
+                    d = f2_fma(f2_splat(dz2[1]), make_float2(w1[2 * j], w1[2 * j + 1]), d);
+                    d = f2_fma(f2_splat(dz2[2]), make_float2(w2r[2 * j], w2r[2 * j + 1]), d);
+                    d = f2_mul(d, f2_splat(scale));
+                    if (!(hv.x > 0.f)) d.x = 0.f;
+                    if (!(hv.y > 0.f)) d.y = 0.f;
+                    o[j] = pack_h2_sat(d.x, d.y);
                 }
                 const uint4 u = make_uint4(o[0], o[1], o[2], o[3]);
                 ep.st_a(ch, u);
