@@ -51,6 +51,7 @@ def test_no_tensor_core_fallbacks_in_binary():
     assert "sm_100a" in sass
     assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
     assert "HMMA." not in sass.replace("UTCHMMA", "")          # no legacy mma.sync path
+    assert "FFMA2" in sass and "FMUL2" in sass                   # packed-fp32 epilogues (Blackwell two-lane fp32)
 
 
 def test_modules_match_reference_contract():
