@@ -383,6 +383,9 @@ def main():
         keys = ("rays_o", "rays_d", "near", "far", "lights_dir", "true_rgb", "mask")
 
         def train(b):
+            # every step starts from weights an optimiser would have just updated: bump the version counters so that nothing
+            # keyed on them (the cached packed weights of the no_grad sampling pass) carries over from the previous step
+            torch.autograd.graph.increment_version(params)
             red.zero()
             out = renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
                                              cos_anneal_ratio=1.0, no_albedo=no_albedo)

@@ -85,7 +85,7 @@ class NeuSRenderer:
             return torch.rand([batch_size, 1], device=device) - 0.5
         return None
 
-    def _sample(self, rays_o, rays_d, near, far, perturb_overwrite):
+    def _sample(self, rays_o, rays_d, near, far, perturb_overwrite, pk=None):
         if self.n_outside > 0:
             raise NotImplementedError(
                 "rnb_b200: render_rnb* with n_outside > 0 has no reference behaviour to match -- the reference's own "
@@ -93,7 +93,7 @@ class NeuSRenderer:
                 "n_outside = 0.  The NeRF++ background is available through render() (reference :556-648).")
         t_rand = self._jitter(len(rays_o), rays_o.device, perturb_overwrite)
         return _ops.hierarchical_sample(self.sdf_network, rays_o, rays_d, near, far, t_rand, self.n_samples,
-                                        self.n_importance, self.up_sample_steps)
+                                        self.n_importance, self.up_sample_steps, pk=pk)
 
     def _outside_z(self, batch_size, far, perturbed, device):
         """stratified inverse-depth samples of the background (reference :562-585): same RNG call as the reference"""
@@ -141,15 +141,18 @@ class NeuSRenderer:
                     cos_anneal_ratio, no_albedo, _z_vals=None):
         # background_rgb is accepted and ignored exactly like the reference (render_core_mvps never reads it)
         batch_size = len(rays_o)
+        # training: ONE weight-norm fold + pack per step, shared by the no_grad sampling pass and the fine pass
+        folded = _ops.fold_and_pack(self.sdf_network) if torch.is_grad_enabled() else None
+        pk = folded[1] if folded is not None else None
         if _z_vals is None:
-            z_vals, mid_z = self._sample(rays_o, rays_d, near, far, perturb_overwrite)
+            z_vals, mid_z = self._sample(rays_o, rays_d, near, far, perturb_overwrite, pk=pk)
         else:       # parity tests: fine pass on caller-provided sample depths
             z_vals, mid_z = _K.final_merge(_z_vals.float().contiguous(), None, 2.0 / self.n_samples)
         n_samples = z_vals.shape[1]
         (color_fine, weight_sum, gradient_error, weights, cdf, inside, weight_max, gradients, sdf,
          _albedo) = _ops.rnb_fine(self.sdf_network, self.color_network, self.deviation_network.variance, rays_o, rays_d,
                                   z_vals, mid_z, lights_dir, cos_anneal_ratio, 1 if warmup else 0, not no_albedo,
-                                  2.0 / self.n_samples)
+                                  2.0 / self.n_samples, folded=folded)
         inv_s = torch.exp(self.deviation_network.variance.detach() * 10.0).clip(1e-6, 1e6)
         s_val = (1.0 / inv_s).expand(batch_size, 1)
         return {

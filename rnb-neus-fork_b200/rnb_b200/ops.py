@@ -52,6 +52,21 @@ def packed_sdf_nograd(sdf_module):
     return cache[1]
 
 
+def fold_and_pack(sdf_module):
+    """One weight-norm fold + one pack for a whole training step: -> (flat, pk).  `flat` are the effective weights WITH
+    their autograd graph (the fine pass differentiates through them), `pk` the packed operands built from the same
+    tensors; the no_grad sampling pass and the fine pass both use `pk`, instead of one fold + pack each
+    (the reference re-folds inside every SDFNetwork.forward call, models/fields.py:72-74)."""
+    flat = _sdf_wb(sdf_module)
+    L.require_cuda(flat[0], "SDFNetwork")
+    with torch.no_grad():
+        pk = _pack_sdf(flat, flat[0].device)
+    if not torch.cuda.is_current_stream_capturing():
+        params = list(sdf_module.parameters())
+        sdf_module._rnb_packed = (tuple((p.data_ptr(), p._version) for p in params), pk)
+    return flat, pk
+
+
 # ------------------------------------------------------------------------------------------ module-level API
 def sdf_only(sdf_module, x):
     """SDFNetwork.sdf under no_grad -> [N,1]"""
@@ -176,9 +191,11 @@ def render_with_background(renderer, rays_o, rays_d, z_vals, mid_z, z_outside, c
 
 # ------------------------------------------------------------------------------------------ sampling
 @torch.no_grad()
-def hierarchical_sample(sdf_module, rays_o, rays_d, near, far, t_rand, n_samples, n_importance, up_sample_steps):
-    """The no_grad block of render*/render_rnb* (reference models/renderer.py:829-880): -> (z_vals, mid_z_vals)."""
-    pk = packed_sdf_nograd(sdf_module)
+def hierarchical_sample(sdf_module, rays_o, rays_d, near, far, t_rand, n_samples, n_importance, up_sample_steps, pk=None):
+    """The no_grad block of render*/render_rnb* (reference models/renderer.py:829-880): -> (z_vals, mid_z_vals).
+    pk: packed operands of this step (fold_and_pack), else the cached no_grad pack."""
+    if pk is None:
+        pk = packed_sdf_nograd(sdf_module)
     o = rays_o.detach().float().contiguous()
     d = rays_d.detach().float().contiguous()
     B = o.shape[0]
@@ -214,7 +231,7 @@ class _RnbFine(torch.autograd.Function):
         sdf_flat = wb[:18]
         col_flat = wb[18:]
         use_albedo = meta["use_albedo"]
-        pk = _pack_sdf(sdf_flat, dev)
+        pk = meta.get("pk") or _pack_sdf(sdf_flat, dev)
         pts = K.points_rays(rays_o, rays_d, mid_z)
         sdf, grad, _, streams = K.sdf_fwd_grad(pk, pts)
         albedo = None
@@ -296,18 +313,18 @@ def _rnb_fine_inference(sdf_module, color_module, variance, o, d, z_vals, mid_z,
 
 
 def rnb_fine(sdf_module, color_module, variance, rays_o, rays_d, z_vals, mid_z, lights, cos_anneal_ratio, mode,
-             use_albedo, sample_dist):
-    """mode 0: render_rnb, 1: render_rnb_warmup, 2: plain colour (render)."""
+             use_albedo, sample_dist, folded=None):
+    """mode 0: render_rnb, 1: render_rnb_warmup, 2: plain colour (render).  folded: (flat, pk) of fold_and_pack."""
     if z_vals.shape[1] != FINE_SAMPLES:
         raise RuntimeError(f"rnb_b200: the fine pass is specialised for n_samples + n_importance = {FINE_SAMPLES} "
                            f"(got {z_vals.shape[1]})")
-    flat = _sdf_wb(sdf_module)
+    flat, pk = folded if folded is not None else (_sdf_wb(sdf_module), None)
     col = []
     if use_albedo:
         for W, b in color_module.effective_weights():
             col += [W, b]
     meta = dict(use_albedo=use_albedo, cos_anneal_ratio=float(cos_anneal_ratio), mode=int(mode),
-                sample_dist=float(sample_dist))
+                sample_dist=float(sample_dist), pk=pk)
     o = rays_o.detach().float().contiguous()
     d = rays_d.detach().float().contiguous()
     needs_grad = torch.is_grad_enabled() and (variance.requires_grad or any(t.requires_grad for t in flat + col))
