@@ -216,6 +216,11 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
 #ifdef RNB_TRACE
     P.tab.trace = g_trace;
 #endif
+    // a_5 and a_6 are re-read by the dx-chain only 3-5 steps after they were written: stored evict-first they are dropped
+    // from L2 right after the producer's prefetch found them still present, and the epilogue then waits for DRAM
+    // (clock64 trace: those two steps 10.6 k / 9.0 k -> 7.3 k / 7.0 k cycles, the tile 228 k -> 215 k).  Older layers
+    // keep the evict-first policy: keeping more (0x78, 0x7f) pushes the later steps' prefetched lines out instead.
+    { static const int km = getenv("RNB_K2_KEEP") ? (int)strtol(getenv("RNB_K2_KEEP"), nullptr, 0) : 0x60; P.keep_mask = km; }
     add_step(P.tab, SDFW_F8, 256, 256);
     {
         const size_t SS = rnb_stream_bytes(pts->n_pts, 256);

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             for (int l = 0; l < 8; ++l) {
                 ep.wait_acc();
                 uint8_t* st_a_next = P.st_in + (size_t)l * SS;       // in_{l+1} = a_l
+                const bool keep_l = (P.keep_mask >> l) & 1;
                 const float* bl = bias + l * 256;
                 ep.sweep_half_bias(bl, [&](int c0, const float (&z)[16]) {
 #pragma unroll
@@ -223,7 +224,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         ha.x = pack_h2(a[0], a[1]); ha.y = pack_h2(a[2], a[3]); ha.z = pack_h2(a[4], a[5]); ha.w = pack_h2(a[6], a[7]);
                         const int ch = (c0 >> 3) + q;
                         ep.st_a(ch, ha);
-                        st_stream(st_a_next, p, ch, 32, ha);
+                        if (keep_l) *reinterpret_cast<uint4*>(st_a_next + stream_off(p, ch, 32)) = ha;
+                        else st_stream(st_a_next, p, ch, 32, ha);
                     }
                 });
                 if (l == 3 && ep.half == 1) emit_skip_pe(ep, x, st_a_next, p);

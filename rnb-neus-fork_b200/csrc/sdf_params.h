@@ -47,6 +47,7 @@ struct SdfFwdGradParams {
     uint8_t* st_in;            // 8 fp16 streams, index l = in_{l+1} = a_l
     uint8_t* st_w;             // 8 fp16 streams, w_l = s_l * ua_l
     size_t stream_stride;      // bytes of one 256-wide stream = Npad * 512
+    int keep_mask;             // bit l: a_l is stored with the default (write-back) policy instead of evict-first
 };
 
 struct SdfBwdParams {
