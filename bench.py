@@ -9,6 +9,7 @@ Default workload (BASELINE.json configs[3]): wmask_rnb.conf with the albedo netw
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -76,21 +77,53 @@ def loss_fn(out, true_rgb, mask, igr_weight=0.1, mask_weight=0.1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md).  The sampler is started
+    BEFORE the warm-up steps (nvidia-smi needs up to a few hundred ms to come up, longer than a short timed region) and
+    every row carries nvidia-smi's timestamp; `mark_start()` / `mark_end()` bracket the timed region and only rows inside
+    it are used.  If fewer than two rows fall inside (timed region shorter than two sampling periods), the rows of the
+    warm-up steps -- same kernels, same load -- are used as well and `window` says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t_begin = datetime.datetime.now()
+        self.t0 = self.t1 = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
+
+    @staticmethod
+    def _parse(rows, lo, hi):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                t = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
+                if not (lo <= t <= hi):
+                    continue
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for i, nme in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].strip().lower().startswith("active"):
+                    reasons.add(nme)
+        return sm, mx, reasons
+
     def stop(self):
         if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        if self.t1 is None:
+            self.mark_end()
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -99,19 +132,15 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for i, nme in enumerate(names):
-                if len(r) > 3 + i and r[3 + i].strip().lower().startswith("active"):
-                    reasons.add(nme)
+        pad = datetime.timedelta(milliseconds=25)
+        t0 = self.t0 or self.t_begin
+        sm, mx, reasons = self._parse(rows, t0 - pad, self.t1 + pad)
+        window = "timed region"
+        if len(sm) < 2:
+            sm, mx, reasons = self._parse(rows, self.t_begin, self.t1 + pad)
+            window = "warm-up + timed region (timed region shorter than two sampling periods)"
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 def build(device, geometric=True):
@@ -352,12 +381,15 @@ def main():
         bmin, bmax = [-1.01] * 3, [1.01] * 3
         host = torch.empty(x1 - x0, R, R, dtype=torch.float32).pin_memory()
         step = lambda i: grid.sdf_slab(sdf, bmin, bmax, R, x0, x1, out=out)
+        clk = ClockSampler(local)
         for i in range(args.warmup):
             step(i)
-        clk = ClockSampler(local)
         L.profile_enable(True)
         n0 = L.launch_count()
+        sync_all()
+        clk.mark_start()
         ms = timed(step, args.steps)
+        clk.mark_end()
         launches = L.launch_count() - n0
         prof = L.profile_collect()
         L.profile_enable(False)
@@ -405,13 +437,18 @@ def main():
                 red.all_reduce()
                 return loss
             step = lambda i: train(dev_b[i % 4])
+        clk = ClockSampler(local)
         for i in range(args.warmup):
             step(i)
-        clk = ClockSampler(local)
         L.profile_enable(True)
         n0 = L.launch_count()
+        sync_all()
+        clk.mark_start()
         ms = timed(step, args.steps)
+        clk.mark_end()
         launches = L.launch_count() - n0
+        if args.graph:      # replays issue no calls through the C-ABI: count the library kernels captured in the graph
+            launches += gs.launches_per_replay * args.steps
         prof = L.profile_collect()
         L.profile_enable(False)
         clocks = clk.stop()

@@ -175,6 +175,23 @@ typedef struct {
 } rnb_ray_batch_t;
 RNB_API int rnb_ray_batch(const rnb_ray_batch_t* p, void* stream);
 
+/* ---- weight norm of all layers of a network at once (reference models/fields.py:72-74, 161-162: nn.utils.weight_norm on
+ *      every layer; forward hook W = g v / |v|_row per layer and call, backward by autograd).  rnb_weight_norm_fold:
+ *      w[rows,cols] = g[r] * v[r,:] / |v[r,:]|, norm[r] = |v[r,:]| for every layer in ONE launch.  rnb_weight_norm_vjp:
+ *      w holds the incoming dW; dg[r] = <dW,v>/norm, dv = g/norm * (dW - v <dW,v>/norm^2), ONE launch. -------------- */
+#define RNB_WN_MAX_LAYERS 16
+typedef struct {
+    int32_t rows, cols;
+    const float* v;      /* weight_v [rows,cols] */
+    const float* g;      /* weight_g [rows] */
+    float* w;            /* fold: out W [rows,cols];  vjp: in dW [rows,cols] */
+    float* norm;         /* fold: out [rows];  vjp: in */
+    float* dv;           /* vjp: out [rows,cols] */
+    float* dg;           /* vjp: out [rows] */
+} rnb_wn_layer_t;
+RNB_API int rnb_weight_norm_fold(const rnb_wn_layer_t* layers, int n_layers, void* stream);
+RNB_API int rnb_weight_norm_vjp(const rnb_wn_layer_t* layers, int n_layers, void* stream);
+
 /* ---- step epilogue (reference exp_runner.py:115 torch.optim.Adam over 61 parameter tensors, :263
  *      optimizer.step()).  One launch over flat fp32 buffers of n elements (16-byte aligned): param, grad, exp_avg and
  *      exp_avg_sq, torch.optim.Adam arithmetic with amsgrad off and weight_decay 0; `step` is the 1-based step count

@@ -42,6 +42,8 @@ cudaError_t launch_composite_bg(const rnb_composite_bg_t& P, cudaStream_t st);
 cudaError_t launch_ray_batch(const rnb_ray_batch_t& P, cudaStream_t st);
 cudaError_t launch_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                              double eps, int64_t step, double grad_scale, int sm_count, cudaStream_t st);
+cudaError_t launch_wn_fold(const rnb_wn_layer_t* layers, int n, cudaStream_t st);
+cudaError_t launch_wn_vjp(const rnb_wn_layer_t* layers, int n, cudaStream_t st);
 cudaError_t launch_mc_count(const float* u, int nx, int ny, int nz, float thr, const int8_t* tri_count, int32_t* counts, cudaStream_t st);
 cudaError_t launch_mc_emit(const float* u, int nx, int ny, int nz, float thr, const int8_t* tri_table, const int64_t* offsets,
                            int x_global0, float* verts, int64_t* keys, cudaStream_t st);
@@ -102,10 +104,10 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
 // ---- optional per-kernel timing (cudaEvents on the launch stream) and a launch counter ------------------------
 enum ProfTag { T_SDF_PACK, T_SDF_FWD, T_SDF_FWD_GRAD, T_SDF_BWD_DATA, T_DW_GEMM, T_COLSUM, T_REDUCE, T_ABSMAX, T_SUM,
                T_COARSE_Z, T_UPSAMPLE, T_FINAL_MERGE, T_COMPOSITE_FWD, T_COMPOSITE_BWD, T_ALBEDO_PACK, T_ALBEDO_FWD,
-               T_ALBEDO_BWD, T_SAMPLE_PDF, T_NERF_PACK, T_NERF_FWD, T_COMPOSITE_BG, T_RAY_BATCH, T_MC, T_ADAM, T_COUNT };
+               T_ALBEDO_BWD, T_SAMPLE_PDF, T_NERF_PACK, T_NERF_FWD, T_COMPOSITE_BG, T_RAY_BATCH, T_MC, T_ADAM, T_WNORM, T_COUNT };
 static const char* const kProfNames[T_COUNT] = {
     "sdf_pack", "sdf_fwd", "sdf_fwd_grad", "sdf_bwd_data", "dw_gemm", "colsum", "reduce", "absmax", "sum", "coarse_z",
-    "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf", "nerf_pack", "nerf_fwd", "composite_bg", "ray_batch", "marching_cubes", "adam"};
+    "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf", "nerf_pack", "nerf_fwd", "composite_bg", "ray_batch", "marching_cubes", "adam", "weight_norm"};
 struct ProfRec { int tag; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -396,6 +398,12 @@ int rnb_mc_emit(const float* u, int nx, int ny, int nz, float threshold, const i
                 int x_global0, float* verts, int64_t* keys, void* stream) {
     return (int)profiled(T_MC, (cudaStream_t)stream, [&] {
         return launch_mc_emit(u, nx, ny, nz, threshold, tri_table, offsets, x_global0, verts, keys, (cudaStream_t)stream); });
+}
+int rnb_weight_norm_fold(const rnb_wn_layer_t* layers, int n_layers, void* stream) {
+    return (int)profiled(T_WNORM, (cudaStream_t)stream, [&] { return launch_wn_fold(layers, n_layers, (cudaStream_t)stream); });
+}
+int rnb_weight_norm_vjp(const rnb_wn_layer_t* layers, int n_layers, void* stream) {
+    return (int)profiled(T_WNORM, (cudaStream_t)stream, [&] { return launch_wn_vjp(layers, n_layers, (cudaStream_t)stream); });
 }
 int rnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, int64_t step, double grad_scale, void* stream) {

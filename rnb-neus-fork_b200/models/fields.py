@@ -10,6 +10,8 @@ reference exp_runner.py:355-386) load unchanged in both directions.
 import math
 
 import numpy as np
+import os as _os
+
 import torch
 import torch.nn as nn
 
@@ -26,14 +28,32 @@ def _wn_linear(n_in, n_out, weight_norm):
     return lin, weight_norm
 
 
+def _use_fused_weight_norm():
+    """The fused fold / VJP replaces 24 small launches per step by 2, which is GPU time saved (graphed 512-ray step 1.57 ->
+    1.51 ms), but its Python autograd node costs more host time than torch's C++ per-layer ops: the eager 512-ray step,
+    which is host-bound, went 2.5 -> 3.5 ms with it.  So it is used where host time does not count -- inside CUDA-graph
+    capture -- unless RNB_FUSED_WN=1 / 0 forces it on / off."""
+    force = _os.environ.get("RNB_FUSED_WN")
+    if force is not None:
+        return force not in ("0", "")
+    return torch.cuda.is_current_stream_capturing()
+
+
 class _WeightNormMLP(nn.Module):
     """Shared plumbing: layers are attributes lin0..linN-1 (legacy weight_norm => weight_g/weight_v)."""
 
     def effective_weights(self):
-        """[(W_l fp32 [out,in], b_l)] with weight-norm folded by torch (autograd gives dg, dv from dW)."""
+        """[(W_l fp32 [out,in], b_l)] with weight-norm folded (reference models/fields.py:72-74); autograd turns the
+        kernels' dW into (dg, dv).  While a CUDA graph is being captured all layers are folded by ONE launch
+        (rnb_b200/wnorm.py) and their VJP is one more; otherwise torch's per-layer _weight_norm is used (see
+        _use_fused_weight_norm)."""
+        lins = [getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)]
+        if all(hasattr(lin, "weight_g") for lin in lins) and lins[0].weight_v.is_cuda and _use_fused_weight_norm():
+            from rnb_b200 import wnorm
+            Ws = wnorm.fold_all([lin.weight_v for lin in lins], [lin.weight_g for lin in lins])
+            return [(W, lin.bias) for W, lin in zip(Ws, lins)]
         out = []
-        for l in range(self.num_layers - 1):
-            lin = getattr(self, "lin" + str(l))
+        for lin in lins:
             if hasattr(lin, "weight_g"):
                 W = torch._weight_norm(lin.weight_v, lin.weight_g, 0)
             else:

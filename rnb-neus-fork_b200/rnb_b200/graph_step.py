@@ -39,9 +39,12 @@ class GraphedTrainStep:
             for _ in range(n_warmup):
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
+        from . import lib as L
         self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
+        self.launches_per_replay = L.launch_count() - n0     # kernels of this library inside the graph (per replay)
 
     def _body(self):
         b = self.static
@@ -49,6 +52,7 @@ class GraphedTrainStep:
         out = self.fn(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"], **self.kw)
         loss = self.loss_fn(out, b["true_rgb"], b["mask"])
         loss.backward()
+        self.red.collect()          # inside the graph: the flat gradient buffer is what a replay leaves behind
         return loss.detach()
 
     def __call__(self, batch):

@@ -62,6 +62,12 @@ class RayBatch(C.Structure):
                 ("lights", C.c_void_p)]
 
 
+class WnLayer(C.Structure):
+    """rnb_wn_layer_t"""
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("v", C.c_void_p), ("g", C.c_void_p), ("w", C.c_void_p),
+                ("norm", C.c_void_p), ("dv", C.c_void_p), ("dg", C.c_void_p)]
+
+
 _lib = None
 
 _VP = C.c_void_p
@@ -98,6 +104,8 @@ _SIGNATURES = {
     "rnb_composite_bg_fwd": (C.c_int, [C.POINTER(CompositeBg), _VP]),
     "rnb_mc_count": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
     "rnb_mc_emit": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, C.c_int, _VP, _VP, _VP]),
+    "rnb_weight_norm_fold": (C.c_int, [C.POINTER(WnLayer), C.c_int, _VP]),
+    "rnb_weight_norm_vjp": (C.c_int, [C.POINTER(WnLayer), C.c_int, _VP]),
     "rnb_adam_step": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                 C.c_int64, C.c_double, _VP]),
     "rnb_ray_batch": (C.c_int, [C.POINTER(RayBatch), _VP]),

@@ -75,16 +75,9 @@ class FlatAdam(torch.optim.Optimizer):
         self.reducer.zero()
 
     def _collect_grads(self):
-        # autograd accumulates in place into the attached views; anything else (a caller that set .grad itself) is folded in
-        for p, v in zip(self.reducer.params, self.reducer.views):
-            g = p.grad
-            if g is v:
-                continue
-            if g is None:
-                v.zero_()
-            elif g.data_ptr() != v.data_ptr():
-                v.copy_(g)
-            p.grad = v
+        # gradients arrive as separate tensors (reducer.zero() unsets .grad so that autograd launches nothing per parameter)
+        # or were assigned by the caller: one multi-tensor copy folds them into the flat buffer
+        self.reducer.collect()
 
     @torch.no_grad()
     def step(self, closure=None):

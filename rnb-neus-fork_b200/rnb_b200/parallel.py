@@ -29,16 +29,45 @@ class FlatGradAllReducer:
         self.attach()
 
     def attach(self):
-        """Point every .grad at its slice of the flat buffer (autograd then accumulates in place)."""
+        """Point every .grad at its slice of the flat buffer."""
         for p, v in zip(self.params, self.views):
             p.grad = v
 
     def zero(self):
-        self.flat.zero_()
+        """Start of a step: gradients are dropped (`.grad = None`), nothing is launched.  With `.grad` unset autograd hands
+        each parameter's gradient over without a kernel; with the views attached it would run one in-place add per
+        parameter (42 tiny launches per train_rnb step).  `collect()` then moves them into the flat buffer in one
+        multi-tensor copy."""
+        for p in self.params:
+            p.grad = None
+        self._collected = False
+
+    def collect(self):
+        """After backward: gather the parameters' gradients into the flat buffer (one foreach copy) and re-attach the
+        views, so `.grad` of every parameter is its slice of `flat`.  Parameters that received no gradient read zero.
+        Idempotent until the next zero()."""
+        if getattr(self, "_collected", False) and all(p.grad is v for p, v in zip(self.params, self.views)):
+            return self.flat
+        dst, src = [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is v:
+                continue
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(g.detach() if g.shape == v.shape else g.detach().reshape(v.shape))
+        if dst:
+            with torch.no_grad():
+                torch._foreach_copy_(dst, src)
         self.attach()
+        self._collected = True
+        return self.flat
 
     def all_reduce(self):
-        """Sum over ranks, divide by the world size.  One collective per step."""
+        """Gather into the flat buffer, sum over ranks, divide by the world size.  One collective per step."""
+        self.collect()
         if not (dist.is_available() and dist.is_initialized()):
             return self.flat
         world = dist.get_world_size(self.group)

@@ -111,9 +111,12 @@ def test_no_grad_fast_path_matches_training_forward():
             assert not out[k].requires_grad
 
 
-def test_graphed_step_matches_eager():
+def test_graphed_step_matches_eager(monkeypatch):
     """the whole step as one CUDA graph (launch-bound 512-ray regime): same loss and gradients as the eager step, also
     after optimiser steps in between (the weight packing is part of the graph)"""
+    # capture folds the weight norm with the fused node; give the eager step the same node so the comparison stays bit-exact
+    # (fused vs per-layer torch fold is compared in test_fused_weight_norm_step_matches_torch_weight_norm)
+    monkeypatch.setenv("RNB_FUSED_WN", "1")
     from rnb_b200.graph_step import GraphedTrainStep
     from rnb_b200.parallel import FlatGradAllReducer
     renderer, sdf, var, col = make_renderer(True)
@@ -131,7 +134,7 @@ def test_graphed_step_matches_eager():
         loss_e = lf(render(renderer, b), b["true_rgb"], b["mask"])
         loss_e.backward()
         assert torch.equal(loss_g, loss_e.detach())
-        assert torch.equal(grads_g, red.flat)
+        assert torch.equal(grads_g, red.collect())
         del loss_e                               # keep no eager autograd graph alive across captures / replays
         opt.step()                               # parameters change in place: the next replay must see them
     # with jitter every replay draws new random numbers
@@ -141,3 +144,32 @@ def test_graphed_step_matches_eager():
     l1 = gs2(b).clone()
     l2 = gs2(b).clone()
     assert torch.isfinite(l1) and torch.isfinite(l2) and not torch.equal(l1, l2)
+
+
+def test_fused_weight_norm_step_matches_torch_weight_norm(monkeypatch):
+    """the whole train step with the fused weight-norm node (used under CUDA-graph capture) gives the gradients of the
+    per-layer torch path, to the bar SURVEY 8c sets for parameter gradients (cosine >= 0.999, rel-L2 <= 1e-2).
+    The two folds round W differently in the last fp32 bit; with beta = 100 softplus and fp16 operands the step amplifies
+    that: moving every weight_g by ONE fp32 ulp under the torch fold changes the gradients by the same amount as switching
+    folds (profiles/_wn_diag.py, 4096 rays: <= 4.7e-3 rel-L2 either way; at 256 rays 1.2e-2 vs 0.8e-2).  So the comparison
+    runs at 4096 rays and is not bit for bit; the node itself is pinned at 1e-5 in
+    test_gpu_sdf.py::test_fused_weight_norm_matches_oracle_and_torch."""
+    renderer, sdf, var, col = make_renderer(True)
+    renderer.perturb = 0.0
+    params = [p for m in (sdf, var, col) for p in m.parameters()]
+    b = batch(4096, seed=3)
+    res = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("RNB_FUSED_WN", flag)
+        for p in params:
+            p.grad = None
+        torch.manual_seed(11)
+        loss = loss_fn(render(renderer, b), b["true_rgb"], b["mask"], 0.1)
+        loss.backward()
+        res.append((float(loss.detach()), [p.grad.clone() for p in params]))
+    assert abs(res[0][0] - res[1][0]) < 1e-4 * abs(res[0][0])
+    for g0, g1 in zip(res[0][1], res[1][1]):
+        assert g0.shape == g1.shape
+        n0, n1 = float(g0.norm()), float(g1.norm())
+        assert float((g0 - g1).norm()) <= 1e-2 * n0 + 1e-12
+        assert float((g0 * g1).sum()) >= 0.999 * n0 * n1

@@ -135,3 +135,32 @@ def test_albedo_fwd_bwd(perturb):
             assert rel_l2(got, want) < 1e-2, (nm, rel_l2(got, want))            # arithmetic, same masks
             assert cosine(got, exact) > 0.999, (nm, cosine(got, exact))         # exact oracle
             assert rel_l2(got, exact) < 3e-2, (nm, rel_l2(got, exact))          # 3000 points, sparse cotangents
+
+
+def test_fused_weight_norm_matches_oracle_and_torch():
+    """rnb_weight_norm_fold / _vjp (all layers in one launch each) vs the oracle (models/fields.py:72-74 restated) and vs
+    torch._weight_norm + autograd, on the shapes of the SDF and albedo networks."""
+    from oracle import rnb_oracle as O
+    from rnb_b200 import wnorm
+    g0 = torch.Generator().manual_seed(3)
+    shapes = [(256, 39), (256, 256), (217, 256), (257, 256), (256, 310), (3, 256)]
+    vs = [torch.randn(s, generator=g0).cuda().requires_grad_(True) for s in shapes]
+    gs = [(torch.rand(s[0], 1, generator=g0) + 0.5).cuda().requires_grad_(True) for s in shapes]
+    dWs = [torch.randn(s, generator=g0).cuda() for s in shapes]
+    Ws = wnorm.fold_all(vs, gs)
+    torch.autograd.backward(Ws[:5], dWs[:5])                     # the last layer receives no gradient (must stay None)
+    vt = [v.detach().clone().requires_grad_(True) for v in vs]
+    gt = [g.detach().clone().requires_grad_(True) for g in gs]
+    Wt = [torch._weight_norm(v, g, 0) for v, g in zip(vt, gt)]
+    torch.autograd.backward(Wt[:5], dWs[:5])
+    for i in range(6):
+        Wo = O.weight_norm_fold(gs[i].detach().cpu().numpy(), vs[i].detach().cpu().numpy())
+        assert rel_l2(Ws[i].detach().cpu().numpy(), Wo) < 1e-6
+        assert torch.allclose(Ws[i], Wt[i], rtol=1e-5, atol=1e-7)
+        if i == 5:
+            assert vs[i].grad is None and gs[i].grad is None      # no cotangent: no gradient, not a zero tensor
+            continue
+        dgo, dvo = O.weight_norm_vjp(gs[i].detach().cpu().numpy(), vs[i].detach().cpu().numpy(), dWs[i].cpu().numpy())
+        assert rel_l2(vs[i].grad.cpu().numpy(), dvo) < 1e-5 and rel_l2(gs[i].grad.cpu().numpy(), dgo) < 1e-5
+        assert gs[i].grad.shape == gs[i].shape
+        assert rel_l2(vs[i].grad.cpu().numpy(), vt[i].grad.cpu().numpy()) < 1e-5

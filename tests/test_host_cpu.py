@@ -164,8 +164,8 @@ def _dp_worker(rank, world, port, q):
     for _ in range(2):                      # second round checks zero() + in-place accumulation
         red.zero()
         net(x).pow(2).mean().backward()
-        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
         red.all_reduce()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
     assert all(v.data_ptr() % 16 == 0 for v in red.views)          # slices are padded to 16-byte boundaries
     q.put((rank, torch.cat([v.reshape(-1) for v in red.views]).numpy(), x.numpy()))
     dist.destroy_process_group()

@@ -58,8 +58,17 @@ def test_flat_adam_host_logic_and_checkpoint_format():
     loss = sum((p ** 2).sum() for p in ps)
     loss.backward()                                            # autograd accumulates into the flat gradient buffer
     assert abs(float(opt.reducer.flat.sum()) - float(sum((2 * p).sum() for p in ps))) < 1e-2
+    opt.zero_grad()                                            # torch semantics (set_to_none): nothing launched
+    assert all(p.grad is None for p in ps)
+    opt.reducer.collect()                                      # no gradient arrived: the flat buffer reads zero
+    assert float(opt.reducer.flat.abs().sum()) == 0.0 and all(p.grad is v for p, v in zip(ps, opt.reducer.views))
     opt.zero_grad()
-    assert float(opt.reducer.flat.abs().sum()) == 0.0 and all(p.grad is not None for p in ps)
+    (ps[0] ** 2).sum().backward()                              # autograd hands the gradient over without a kernel ...
+    assert ps[0].grad is not opt.reducer.views[0]
+    opt.reducer.collect()                                      # ... and one multi-tensor copy gathers it
+    assert ps[0].grad is opt.reducer.views[0] and torch.equal(ps[0].grad, 2 * ps[0].detach())
+    assert float(opt.reducer.views[1].abs().sum()) == 0.0
+    opt.zero_grad()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         opt.step()
     with pytest.raises(NotImplementedError):
@@ -101,7 +110,7 @@ def test_flat_adam_kernel_matches_oracle_and_torch():
         gs = _grads(ps, k)
         opt.zero_grad()
         for p, r, g in zip(ps, ref, gs):
-            p.grad.add_(g)                                     # what autograd does with the attached views
+            p.grad = g.clone()                                 # what autograd does after zero_grad()
             r.grad = g.clone()
         opt.step()
         tadam.step()
@@ -116,7 +125,7 @@ def test_flat_adam_kernel_matches_oracle_and_torch():
     a, b = _params("cuda", 3), _params("cuda", 3)
     oa, ob = FlatAdam(a, lr=1e-3), FlatAdam(b, lr=1e-3, grad_scale=0.5)
     for p, q, g in zip(a, b, _grads(a, 1)):
-        p.grad.add_(g)
+        p.grad.add_(g)                                         # views attached at construction: in-place accumulation
         q.grad.add_(2 * g)
     v0 = a[0]._version
     oa.step()
