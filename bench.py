@@ -37,7 +37,7 @@ FLOP_PER_RAY = {True: 967303168, False: 855433216}          # with / without the
 
 # algorithmic HBM bytes per fine point of the stream-carrying kernels (fp16 streams of 512 B/point,
 # 128 B/point for the 64-wide ones; fp32 per-point inputs/outputs).  ncu's dram__bytes for the same launches are in
-# profiles/r01_ncu_summary.md (sdf_fwd_grad 12.1 KB/point, sdf_bwd_data 25.1 KB/point measured).
+# profiles/r01_ncu_summary_s4.md (sdf_fwd_grad 11.7 KB/point, sdf_bwd_data 25.6 KB/point measured).
 BYTES_PER_POINT = {
     "sdf_fwd_grad": 128 + 8 * 512 + 8 * 512 + 512 + 7 * 512 + 28,           # in0, a_l, w_l, feat written; a_l re-read
     "sdf_bwd_data": (2 * 8 + 8 + 8) * 512 + 512 + 16 + 128 + (8 + 8 + 1) * 512,  # a(x2), w, uin read; uin0, uin, zbar, dfeat written
@@ -46,7 +46,7 @@ BYTES_PER_POINT = {
     "albedo_bwd": 2 * 512 + 3 * 512 + 40,
 }
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per point of the same launches (profiles/)
-NCU_DRAM_BYTES_PER_POINT = {"sdf_fwd_grad": 12090, "sdf_bwd_data": 25080}
+NCU_DRAM_BYTES_PER_POINT = {"sdf_fwd_grad": 11747, "sdf_bwd_data": 25622}     # profiles/r01_ncu_summary_s4.md, 1 048 576 points
 
 WORKLOADS = {
     "dp8192": dict(rays=8192, no_albedo=False, desc="wmask_rnb.conf train_rnb (render_rnb_warmup fwd + loss + bwd + eikonal), "
