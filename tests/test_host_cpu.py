@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 import sys
+import tempfile
 
 import numpy as np
 import pytest
@@ -259,3 +260,43 @@ def test_sharded_mesh_gather_and_weld_gloo_world2():
             de[e] += 1
     und = Counter(tuple(sorted(e)) for e in de)
     assert max(de.values()) == 1 and set(und.values()) == {2} and len(V) - len(und) + len(T) == 2
+
+
+def test_bench_clock_sampler_windows():
+    """bench.py's nvidia-smi sampler: only rows stamped inside the timed region count; with fewer than two of them the
+    warm-up rows (same load) are used and the line says so; throttle reasons come from the rows that were used."""
+    import datetime as dt
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rnb_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    t = dt.datetime(2026, 1, 1, 12, 0, 0)
+    ms = lambda k: dt.timedelta(milliseconds=k)
+    row = lambda k, mhz, cap: [(t + ms(k)).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3], f" {mhz}", " 1965", " 900.0",
+                               " Not Active", " Not Active", " Not Active", " Active" if cap else " Not Active"]
+    rows = [row(0, 1965, False), row(50, 1900, False), row(100, 1700, True), row(150, 1650, True), row(200, 1600, True),
+            ["garbage"], row(250, 1965, False)]
+    sm, mx, reasons = bench.ClockSampler._parse(rows, t + ms(90), t + ms(210))
+    assert sm == [1700.0, 1650.0, 1600.0] and mx == [1965.0] * 3 and reasons == {"sw_power_cap"}
+    sm, mx, reasons = bench.ClockSampler._parse(rows, t + ms(240), t + ms(260))
+    assert sm == [1965.0] and reasons == set()
+
+    class _P:                                   # a finished sampler process
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    def sampler(t0, t1):
+        s = bench.ClockSampler.__new__(bench.ClockSampler)
+        s.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        s.f.write("\n".join(",".join(r) for r in rows) + "\n")
+        s.p, s.t_begin, s.t0, s.t1 = _P(), t - ms(10), t0, t1
+        return s.stop()
+    c = sampler(t + ms(90), t + ms(210))
+    assert c["samples"] == 3 and c["sm_mhz"] == 1650.0 and c["window"] == "timed region" and c["reasons"] == ["sw_power_cap"]
+    c = sampler(t + ms(110), t + ms(120))       # shorter than a sampling period: falls back to warm-up + timed rows
+    assert c["samples"] == 3 and c["window"].startswith("warm-up") and c["sm_mhz"] == 1900.0
