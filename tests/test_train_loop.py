@@ -50,8 +50,11 @@ def test_ply_round_trip():
 
 
 @pytest.mark.gpu
-def test_train_rnb_loop_recovers_sphere_radius():
-    """Geometric init is a sphere of radius 0.5 (SDFNetwork bias, confs/wmask_rnb.conf:61); the scene shows one of radius
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_rnb_loop_recovers_sphere_radius(use_graph):
+    """use_graph: one CUDA graph per mode (warm-up / regular) replayed per iteration, with the fused weight-norm node and
+    the flat gradient gather captured inside and FlatAdam stepping outside -- must train like the eager loop.
+    Geometric init is a sphere of radius 0.5 (SDFNetwork bias, confs/wmask_rnb.conf:61); the scene shows one of radius
     0.62.  A short run of the reference's loop (warm-up renders, then per-pixel lights) must move the zero level set
     towards it, and the mesh extracted afterwards must be a closed surface of that radius."""
     from gpu_common import build_nets
@@ -70,7 +73,8 @@ def test_train_rnb_loop_recovers_sphere_radius():
             return float(sdf.sdf(dirs * 0.62).abs().mean())
     e0 = radius_error()
     assert e0 > 0.08                                                      # the initial surface is 0.12 away
-    _, hist = train_rnb(renderer, [sdf, var, col], scene, n_iters=400, batch_size=512, warm_up_iter=100, report_freq=100)
+    _, hist = train_rnb(renderer, [sdf, var, col], scene, n_iters=400, batch_size=512, warm_up_iter=100, report_freq=100,
+                        use_graph=use_graph)
     e1 = radius_error()
     assert np.isfinite([h[1] for h in hist]).all() and hist[-1][1] < hist[0][1]
     assert e1 < 0.5 * e0, (e0, e1, hist)
