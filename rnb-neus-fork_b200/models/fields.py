@@ -1,17 +1,15 @@
 """SDFNetwork / RenderingNetwork / NeRF / SingleVarianceNetwork with the reference's
 constructor and forward signatures and state_dict keys (reference models/fields.py:8-325),
-evaluated by the sm_100a kernels in rnb_b200 (tcgen05 MLP chains; csrc/mlp_chain.cuh).
+evaluated by the sm_100a kernels in rnb_b200 (tcgen05 MLP chains; csrc/chain.cuh).
 
 Parameters are created with the same torch RNG call sequence as the reference, so
 `torch.manual_seed(s)` gives bit-identical initial weights and reference checkpoints
 (`linK.weight_g / weight_v / bias`, `pts_linears.N.weight`, `variance`;
 reference exp_runner.py:355-386) load unchanged in both directions.
 """
-import math
-
-import numpy as np
 import os as _os
 
+import numpy as np
 import torch
 import torch.nn as nn
 

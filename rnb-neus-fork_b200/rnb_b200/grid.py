@@ -94,7 +94,6 @@ def marching_cubes_device(u, threshold, x_global0=0, weld=True):
     (SURVEY 8f rank 3).  -> (vertices float64 [V,3] in lattice index coordinates, triangles int64 [T,3]) as numpy, the
     return convention of `mcubes.marching_cubes` (reference models/renderer.py:31).  With weld=False returns the raw
     device tensors (verts [T*3,3] float32, keys [T*3] int64) for merging slabs before one global weld."""
-    import ctypes as C
     L.require_cuda(u, "marching_cubes_device")
     u = u.detach().float().contiguous()
     nx, ny, nz = u.shape
