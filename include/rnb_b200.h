@@ -75,6 +75,10 @@ RNB_API int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const f
  * dW, db: HOST arrays of 9 DEVICE pointers, dW[l] fp32 [out_l,in_l] row-major (256x39, 256x256, 256x256,
  * 217x256, 256x256 x4, 257x256), db[l] [out_l]; overwritten. */
 RNB_API size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts);
+/* Diagnostics of the fused backward launch (env RNB_FUSED_DBG=1): byte offset inside `scratch` of uint64 [2][160]
+ * globaltimer stamps (block end times, then block start times), indexed by block: blocks [0, n_workers) are the
+ * weight-gradient workers, the rest the chain blocks. */
+RNB_API size_t rnb_sdf_bwd_debug_offset(int64_t n_pts);
 RNB_API int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
                 const float* d_feat, const void* d_feat16, const float* d_feat16_meta, const void* st_in0,
                 const void* st_in, const void* st_w, void* scratch, float* const* dW, float* const* db, void* stream);

@@ -48,11 +48,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_fwd_kernel(const __gr
     if (warp == 0) {
         if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
     } else if (warp == 1) {
-#ifdef RNB_MMA_V1
-        if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
-#else
         chain_mma_warp(s, P.tab, tmem, n_my);
-#endif
     } else {
         Epi ep;
         ep.init(s, tmem);
@@ -151,11 +147,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
     if (warp == 0) {
         if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
     } else if (warp == 1) {
-#ifdef RNB_MMA_V1
-        if (lane == 0) chain_mma(s, P.tab, tmem, n_my);
-#else
         chain_mma_warp(s, P.tab, tmem, n_my);
-#endif
     } else {
         Epi ep;
         ep.init(s, tmem);

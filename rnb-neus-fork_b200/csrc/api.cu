@@ -16,12 +16,11 @@ cudaError_t launch_sdf_pack(const float* const* W, const float* const* b, uint8_
 cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_sdf_fwd_grad(const SdfFwdGradParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_sdf_bwd_data(const SdfBwdParams& P, int sm_count, cudaStream_t st);
+cudaError_t launch_sdf_bwd_fused(const SdfBwdFusedParams& P, int sm_count, cudaStream_t st);
 cudaError_t launch_dw_gemm(const DwParams& P, int splits, cudaStream_t st);
-cudaError_t launch_colsum(const ColsumParams& P, int splits, cudaStream_t st);
 cudaError_t launch_reduce(const ReduceParams& P, cudaStream_t st);
 cudaError_t launch_absmax(const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
                           const float* fold, float* out, cudaStream_t st);
-cudaError_t launch_sum(const float* x, int64_t n, float* partial, float* out, cudaStream_t st);
 cudaError_t launch_coarse_z(const float* near, const float* far, const float* t_rand, float* z, int n_rays, int n_samples,
                             cudaStream_t st);
 cudaError_t launch_upsample(const UpsampleParams& P, cudaStream_t st);
@@ -51,7 +50,7 @@ cudaError_t launch_stream_from_rowmajor(const float* x, int64_t n, int cols, int
 
 struct AlbedoBwdScratch {
     size_t absmax, sum_part, dz2, dz1, dz0, dw_part, dwcs_part, cs_part, total;
-    int dw_splits, cs_splits;
+    int dw_splits;
 };
 static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
     AlbedoBwdScratch L;
@@ -59,7 +58,6 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
     const int64_t n_pad = rnb_padded_points(n_pts);
     const int n_sub = (int)(n_pad / 64);
     L.dw_splits = std::max(1, std::min(n_sub, 96));
-    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 96));
     size_t o = 0;
     L.absmax = o; o += 256;
     L.sum_part = o; o += 3 * 256;
@@ -68,23 +66,22 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
     L.dz0 = o; o += s256;
     o = align_up(o, 256);
     L.dw_part = o; o += (size_t)L.dw_splits * 256 * (256 + 256 + 64) * 4;
-    L.dwcs_part = o; o += (size_t)L.dw_splits * 256 * 2 * 4;
-    L.cs_part = o; o += (size_t)L.cs_splits * 256 * 5 * 4;
+    L.dwcs_part = o; o += (size_t)2 * L.dw_splits * 256 * 2 * 4;      // two column-sum partials per split (dw_gemm_kernel)
+    L.cs_part = o; o += (size_t)2 * L.dw_splits * (3 * 256 + 4) * 4;  // W_2: three weighted sums + the weight sums
     L.total = align_up(o, 256);
     return L;
 }
 
 // scratch layout of rnb_sdf_bwd
 struct SdfBwdScratch {
-    size_t absmax, sum_part, uin0, uin, zbar, dfeat, dw_part, dwcs_part, cs_part, total;
-    int dw_splits, cs_splits;
+    size_t absmax, sum_part, uin0, uin, zbar, dfeat, dw_part, dwcs_part, cs_part, queue, total;
+    int dw_splits;
 };
 static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     SdfBwdScratch L;
     const size_t s256 = rnb_stream_bytes(n_pts, 256), s64 = rnb_stream_bytes(n_pts, 64);
     const int n_sub = (int)(rnb_padded_points(n_pts) / 64);
     L.dw_splits = std::max(1, std::min(n_sub, 48));
-    L.cs_splits = std::max(1, std::min(n_sub / 4 + 1, 96));
     size_t o = 0;
     L.absmax = o; o += 256;
     L.sum_part = o; o += 256;
@@ -94,19 +91,40 @@ static SdfBwdScratch sdf_bwd_scratch(int64_t n_pts) {
     L.dfeat = o; o += s256;
     o = align_up(o, 256);
     L.dw_part = o; o += (size_t)L.dw_splits * 256 * (64 + 8 * 256) * 4;
-    L.dwcs_part = o; o += (size_t)L.dw_splits * 256 * 9 * 4;
-    L.cs_part = o; o += (size_t)L.cs_splits * 256 * 12 * 4;
+    // column-sum partials: two per split (the two warp groups of dw_gemm_kernel each sum half of the point rows)
+    L.dwcs_part = o; o += (size_t)2 * L.dw_splits * 256 * 9 * 4;
+    L.cs_part = o; o += (size_t)2 * L.dw_splits * (2 * 256 + 4) * 4;  // sdf row of W_8: two sums + the weight sum
+    o = align_up(o, 256);
+    // fused backward: counters (head[9], tail[9], padded to 64 ints) + the per-layer hand-over queues [9][n_tiles]
+    L.queue = o; o += (64 + (size_t)18 * (rnb_padded_points(n_pts) / TILE_M)) * 4 + 2 * FUSED_MAX_WORKERS * 8;
     L.total = align_up(o, 256);
     return L;
 }
 
+// Workers of the fused backward per layer (layer 0 and 8 contract less: N = 64 / one stream pair).  RNB_DW_REPL overrides
+// ("3,4,4,4,4,4,4,4,2"); the sum is the number of SMs taken from the chain.  Each count is clamped to dw_splits.
+static void fused_replicas(int (&rep)[9], int max_rep) {
+    static const int def[9] = {3, 4, 4, 4, 4, 4, 4, 4, 2};
+    for (int l = 0; l < 9; ++l) rep[l] = def[l];
+    if (const char* e = getenv("RNB_DW_REPL")) {
+        int l = 0;
+        const char* p = e;
+        while (*p && l < 9) {
+            rep[l++] = atoi(p);
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+    }
+    for (int l = 0; l < 9; ++l) rep[l] = std::max(1, std::min(rep[l], std::min(max_rep, 16)));
+}
+
 
 // ---- optional per-kernel timing (cudaEvents on the launch stream) and a launch counter ------------------------
-enum ProfTag { T_SDF_PACK, T_SDF_FWD, T_SDF_FWD_GRAD, T_SDF_BWD_DATA, T_DW_GEMM, T_COLSUM, T_REDUCE, T_ABSMAX, T_SUM,
+enum ProfTag { T_SDF_PACK, T_SDF_FWD, T_SDF_FWD_GRAD, T_SDF_BWD_DATA, T_SDF_BWD_FUSED, T_DW_GEMM, T_REDUCE, T_ABSMAX,
                T_COARSE_Z, T_UPSAMPLE, T_FINAL_MERGE, T_COMPOSITE_FWD, T_COMPOSITE_BWD, T_ALBEDO_PACK, T_ALBEDO_FWD,
                T_ALBEDO_BWD, T_SAMPLE_PDF, T_NERF_PACK, T_NERF_FWD, T_COMPOSITE_BG, T_RAY_BATCH, T_MC, T_ADAM, T_WNORM, T_COUNT };
 static const char* const kProfNames[T_COUNT] = {
-    "sdf_pack", "sdf_fwd", "sdf_fwd_grad", "sdf_bwd_data", "dw_gemm", "colsum", "reduce", "absmax", "sum", "coarse_z",
+    "sdf_pack", "sdf_fwd", "sdf_fwd_grad", "sdf_bwd_data", "sdf_bwd_fused", "dw_gemm", "reduce", "absmax", "coarse_z",
     "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf", "nerf_pack", "nerf_fwd", "composite_bg", "ray_batch", "marching_cubes", "adam", "weight_norm"};
 struct ProfRec { int tag; cudaEvent_t a, b; };
 static bool g_prof_on = false;
@@ -238,6 +256,13 @@ int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const float* au
 
 
 size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts) { return sdf_bwd_scratch(n_pts).total; }
+// byte offset, inside the scratch buffer, of the fused backward's optional block time stamps (RNB_FUSED_DBG=1):
+// uint64 [2][160] globaltimer ns, end times then start times, indexed by block
+size_t rnb_sdf_bwd_debug_offset(int64_t n_pts) {
+    const SdfBwdScratch L = sdf_bwd_scratch(n_pts);
+    const size_t nt = (size_t)(rnb_padded_points(n_pts) / TILE_M);
+    return (L.queue + (64 + 18 * nt) * 4 + 7) & ~(size_t)7;
+}
 
 int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, const float* d_sdf, const float* d_grad,
                 const float* d_feat, const void* d_feat16, const float* d_feat16_meta, const void* st_in0,
@@ -292,8 +317,15 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     P.st_in = (const uint8_t*)st_in; P.st_w = (const uint8_t*)st_w;
     P.st_uin0 = sc + L.uin0; P.st_uin = sc + L.uin; P.st_zbar = sc + L.zbar; P.st_dfeat = sc + L.dfeat;
     P.stream_stride = SS;
-    e = profiled(T_SDF_BWD_DATA, st, [&] { return launch_sdf_bwd_data(P, sm_count(), st); });
-    if (e != cudaSuccess) return (int)e;
+    // RNB_BWD_FUSED=1: one launch for K3a + K3b (sdf_bwd_fused_kernel, the weight-gradient workers take the cotangent
+    // streams over through L2).  Measured (profiles/r02_notes.md): parity-green but not faster -- with ~230 tiles in flight the
+    // hand-over set exceeds what L2 retains, DRAM reads drop only 35.6 -> 32 GB and the chain loses the workers' SMs -- so the
+    // two-kernel path stays the default.
+    const bool fused = getenv("RNB_BWD_FUSED") && atoi(getenv("RNB_BWD_FUSED")) != 0;
+    if (!fused) {
+        e = profiled(T_SDF_BWD_DATA, st, [&] { return launch_sdf_bwd_data(P, sm_count(), st); });
+        if (e != cudaSuccess) return (int)e;
+    }
     // ---- K3b: dW_l = w_l^T uin_l + zbar_l^T in_l  (l = 0..7),  dW_8[1:] = dfeat^T in_8
     const int n_sub = (int)(rnb_padded_points(n) / 64);
     DwParams D{};
@@ -302,72 +334,106 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     R.cot_absmax = absmax;
     float* part = (float*)(sc + L.dw_part);
     float* dwcs = (float*)(sc + L.dwcs_part);
+    int rep[9];
+    fused_replicas(rep, L.dw_splits);
     const uint8_t* in0 = (const uint8_t*)st_in0;
     const uint8_t* inl = (const uint8_t*)st_in;
     const uint8_t* sw = (const uint8_t*)st_w;
-    for (int l = 0; l < 9; ++l) {
-        DwJob& j = D.jobs[D.n_jobs++];
+    float* cpart = (float*)(sc + L.cs_part);      // [2][2 dw_splits][256]: the two sums of the sdf row of W_8
+    const int cs_mul = fused ? 1 : 2;             // column-sum partials per split (dw_gemm_kernel: one per warp group)
+    const size_t cs_stride = (size_t)2 * L.dw_splits * 256;
+    // layer 8 first: its CTAs take three column sums per tile and must not form the tail of the launch
+    for (int li = 0; li < 9; ++li) {
+        const int l = li == 0 ? 8 : li - 1;
+        DwJob& j = D.jobs[fused ? l : D.n_jobs];
+        ++D.n_jobs;
         j.nw = l == 0 ? 64 : 256;
         j.b_chunk0 = 0;
+        const int splits = fused ? rep[l] : L.dw_splits;
         if (l < 8) {
-            j.n_pairs = 2;
+            j.n_pairs = j.mma_pairs = 2;
             j.a[0] = sw + (size_t)l * SS;
             j.b[0] = l == 0 ? sc + L.uin0 : sc + L.uin + (size_t)(l - 1) * SS;
             j.a[1] = sc + L.zbar + (size_t)l * SS;
             j.b[1] = l == 0 ? in0 : inl + (size_t)(l - 1) * SS;
         } else {
-            j.n_pairs = 1;
+            j.n_pairs = j.mma_pairs = 1;          // dW_8[1:,:] = dfeat^T a_7
             j.a[0] = sc + L.dfeat;
             j.b[0] = inl + (size_t)7 * SS;
         }
-        j.b_chunks[0] = j.b_chunks[1] = j.nw / 8;
+        for (int k = 0; k < DW_MAX_PAIRS; ++k) j.b_chunks[k] = j.nw / 8;
         j.partial = part;
         // bias gradient db_l = column sums of zbar_l (dfeat for l = 8), taken from the staged A tile inside the GEMM
-        j.colsum_pair = l < 8 ? 1 : 0;
-        j.cs_partial = dwcs;
         {
+            DwColsum& c = j.cs[j.n_cs++];
+            c.pair = l < 8 ? 1 : 0; c.tile_off = 0; c.width = 256; c.n_w = 0; c.partial[0] = dwcs;
             ReduceJob& rb = R.jobs[R.n_jobs++];
-            rb.partial = dwcs; rb.splits = L.dw_splits; rb.rows = 1; rb.nw = 256;
+            rb.partial = dwcs; rb.splits = cs_mul * splits; rb.rows = 1; rb.nw = 256;
             rb.dst = db[l]; rb.dst_pitch = 0; rb.dst_row0 = 0; rb.dst_col0 = l == 8 ? 1 : 0;
             rb.out_rows = 1; rb.out_cols = l == 3 ? 217 : 256; rb.factor = 1.f; rb.use_cot_scale = 1;
-            dwcs += (size_t)L.dw_splits * 256;
+            dwcs += cs_stride;
+        }
+        // dW_8[0,:] = sum_p uabar_7[p,:]  +  sum_p d_sdf[p] a_7[p,:]   (models/fields.py:104: sdf = row 0 of lin8)
+        float* p0 = cpart;                  // [2 dw_splits][256]  first sum, taken by layer 0's CTAs
+        float* p1 = cpart + cs_stride;      //                     second sum (+ the weight sum), taken by layer 8's CTAs
+        if (l == 0) {
+            // uabar_7 (= the uin_8 stream) is no GEMM operand anywhere: its two 128-column halves ride in the 24 KB that
+            // layer 0's 64-wide B operands leave free in the two stages of every sub-tile
+            for (int pr = 0; pr < 2; ++pr) {
+                j.x[pr] = sc + L.uin + (size_t)7 * SS;
+                j.x_chunk0[pr] = 16 * pr;
+                DwColsum& c = j.cs[j.n_cs++];
+                c.pair = pr; c.tile_off = 32768 + 8 * 1024; c.width = 128; c.col0 = 128 * pr; c.n_w = 0; c.partial[0] = p0;
+            }
+        }
+        if (l == 8) {
+            DwColsum& c1 = j.cs[j.n_cs++];
+            c1.pair = 0; c1.tile_off = 32768; c1.width = 256; c1.n_w = 1; c1.w[0] = d_sdf; c1.n_valid = n; c1.partial[0] = p1;
+            // db_8[0] = sum_p d_sdf[p]: the sum of the weights of the same pass
+            c1.wsum_partial = cpart + 2 * cs_stride;
+            ReduceJob& rs = R.jobs[R.n_jobs++];
+            rs.partial = c1.wsum_partial; rs.splits = cs_mul * splits; rs.rows = 1; rs.nw = 4;
+            rs.dst = db[8]; rs.dst_pitch = 0; rs.out_rows = 1; rs.out_cols = 1; rs.factor = 1.f; rs.use_cot_scale = 0;
+            ReduceJob& r = R.jobs[R.n_jobs++];
+            r.partial = p0; r.splits = cs_mul * (fused ? rep[0] : L.dw_splits); r.rows = 1; r.nw = 256;
+            r.dst = dW[8]; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = 1;
+            r.partial2 = p1; r.splits2 = cs_mul * splits; r.factor2 = 1.f; r.use_cot_scale2 = 0;
         }
         ReduceJob& r = R.jobs[R.n_jobs++];
-        r.partial = part; r.splits = L.dw_splits; r.rows = 256; r.nw = j.nw;
+        r.partial = part; r.splits = splits; r.rows = 256; r.nw = j.nw;
         r.dst = dW[l]; r.dst_pitch = l == 0 ? 39 : 256; r.dst_row0 = l == 8 ? 1 : 0; r.dst_col0 = 0;
         r.out_rows = l == 3 ? 217 : 256; r.out_cols = l == 0 ? 39 : 256;
         r.factor = l == 4 ? 0.70710678118654752f : 1.f;
         r.use_cot_scale = 1; r.fold_xlo = l == 0; r.accumulate = 0;
         part += (size_t)L.dw_splits * 256 * j.nw;
     }
-    e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
-    if (e != cudaSuccess) return (int)e;
-    // ---- bias gradients and the sdf row of W_8 (column sums over streams)
-    ColsumParams C{};
-    C.n_sub = n_sub;
-    C.n_pts = n;
-    float* cpart = (float*)(sc + L.cs_part);
-    auto add_cs = [&](const uint8_t* stream, const float* wgt) {
-        ColsumJob& j = C.jobs[C.n_jobs++];
-        j.stream = stream; j.chunks = 32; j.n_w = 1; j.row_weight[0] = wgt; j.partial[0] = cpart;
-        float* p0 = cpart;
-        cpart += (size_t)L.cs_splits * 256;
-        return p0;
-    };
-    {
-        // dW_8[0,:] = sum_p uabar_7[p,:]  +  sum_p d_sdf[p] a_7[p,:]
-        const float* p0 = add_cs(sc + L.uin + (size_t)7 * SS, nullptr);
-        const float* p1 = add_cs(inl + (size_t)7 * SS, d_sdf);
-        ReduceJob& r = R.jobs[R.n_jobs++];
-        r.partial = p0; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
-        r.dst = dW[8]; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = 1;
-        r.partial2 = p1; r.splits2 = L.cs_splits; r.factor2 = 1.f; r.use_cot_scale2 = 0;
+    if (fused) {
+        SdfBwdFusedParams F{};
+        F.chain = P;
+        F.chain.keep_streams = getenv("RNB_FUSED_KEEP") ? atoi(getenv("RNB_FUSED_KEEP")) : 1;
+        int* qmem = (int*)(sc + L.queue);
+        // [head 16 | tail 16 | pad 32 | cnt 9 n_tiles | q 9 n_tiles | dbg]
+        F.q_head = qmem; F.q_tail = qmem + 16; F.q_cnt = qmem + 64; F.q = F.q_cnt + (size_t)9 * P.n_tiles;
+        e = cudaMemsetAsync(qmem, 0, (64 + (size_t)9 * P.n_tiles) * sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemsetAsync(F.q, 0xff, (size_t)9 * P.n_tiles * sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+        F.stagger_ns = getenv("RNB_FUSED_STAGGER_US") ? 1000 * atoi(getenv("RNB_FUSED_STAGGER_US")) : 150000;
+        if (P.n_tiles < 4 * sm_count()) F.stagger_ns = 0;           // a couple of tiles per CTA: nothing to de-phase
+        if (getenv("RNB_FUSED_DBG")) F.dbg = (unsigned long long*)(((uintptr_t)(F.q + (size_t)9 * P.n_tiles) + 7) & ~(uintptr_t)7);
+        for (int l = 0; l < 9; ++l) F.jobs[l] = D.jobs[l];      // (fused: D.jobs is indexed by layer)
+        for (int l = 0; l < 9; ++l)
+            for (int r = 0; r < rep[l]; ++r) {
+                F.dw_layer[F.n_dw] = (uint8_t)l;
+                F.dw_replica[F.n_dw] = (uint8_t)r;
+                ++F.n_dw;
+            }
+        e = profiled(T_SDF_BWD_FUSED, st, [&] { return launch_sdf_bwd_fused(F, sm_count(), st); });
+    } else {
+        e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
     }
-    e = profiled(T_COLSUM, st, [&] { return launch_colsum(C, L.cs_splits, st); });
     if (e != cudaSuccess) return (int)e;
-    e = profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
-    if (e != cudaSuccess) return (int)e;
-    return (int)profiled(T_SUM, st, [&] { return launch_sum(d_sdf, n, (float*)(sc + L.sum_part), db[8], st); });
+    return (int)profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
 }
 
 
@@ -529,55 +595,51 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     float* part = (float*)(sc + L.dw_part);
     float* dwcs = (float*)(sc + L.dwcs_part);
     auto add_dw = [&](const uint8_t* a, const uint8_t* b, int b_chunks, int nw, float* dst, int pitch, int col0, int out_cols,
-                      float* db_dst) {
+                      float* db_dst) -> DwJob& {
         DwJob& j = D.jobs[D.n_jobs++];
-        j.n_pairs = 1; j.a[0] = a; j.b[0] = b; j.b_chunks[0] = b_chunks; j.b_chunk0 = 0; j.nw = nw; j.partial = part;
-        j.colsum_pair = -1;
+        j.n_pairs = j.mma_pairs = 1; j.a[0] = a; j.b[0] = b; j.b_chunk0 = 0; j.nw = nw; j.partial = part;
+        for (int k = 0; k < DW_MAX_PAIRS; ++k) j.b_chunks[k] = b_chunks;
         if (db_dst) {
-            j.colsum_pair = 0;
-            j.cs_partial = dwcs;
+            DwColsum& c = j.cs[j.n_cs++];
+            c.pair = 0; c.tile_off = 0; c.width = 256; c.n_w = 0; c.partial[0] = dwcs;
             ReduceJob& rb = R.jobs[R.n_jobs++];
-            rb.partial = dwcs; rb.splits = L.dw_splits; rb.rows = 1; rb.nw = 256;
+            rb.partial = dwcs; rb.splits = 2 * L.dw_splits; rb.rows = 1; rb.nw = 256;
             rb.dst = db_dst; rb.dst_pitch = 0; rb.out_rows = 1; rb.out_cols = 256; rb.factor = 1.f; rb.use_cot_scale = 1;
-            dwcs += (size_t)L.dw_splits * 256;
+            dwcs += (size_t)2 * L.dw_splits * 256;
         }
         ReduceJob& r = R.jobs[R.n_jobs++];
         r.partial = part; r.splits = L.dw_splits; r.rows = 256; r.nw = nw;
         r.dst = dst; r.dst_pitch = pitch; r.dst_row0 = 0; r.dst_col0 = col0; r.out_rows = 256; r.out_cols = out_cols;
         r.factor = 1.f; r.use_cot_scale = 1;
         part += (size_t)L.dw_splits * 256 * nw;
+        return j;
     };
-    add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256, db1);
+    DwJob& j1 = add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256, db1);
     add_dw(sc + L.dz0, (const uint8_t*)st_feat, 32, 256, dW0, 310, 54, 256, db0);
     add_dw(sc + L.dz0, (const uint8_t*)st_pe, 8, 64, dW0, 310, 0, 54, nullptr);
-    e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
-    if (e != cudaSuccess) return (int)e;
-    ColsumParams C{};
-    C.n_sub = n_sub;
-    C.n_pts = n_pad;
-    float* cpart = (float*)(sc + L.cs_part);
     {
-        // dW_2[k,:] = sum_p dz2[k,p] h1[p,:], k = 0..2: three weighted column sums in ONE pass over the h1 stream
-        ColsumJob& j = C.jobs[C.n_jobs++];
-        j.stream = (const uint8_t*)st_h1; j.chunks = 32; j.n_w = 3;
+        // dW_2[k,:] = sum_p dz2[k,p] h_1[p,:] and db_2[k] = sum_p dz2[k,p], k = 0..2 (the 3-wide output layer,
+        // models/fields.py:203-214): the first job also stages the h_1 tiles and takes three weighted column sums
+        j1.n_pairs = 2;
+        j1.a[1] = (const uint8_t*)st_h1;
+        DwColsum& c = j1.cs[j1.n_cs++];
+        c.pair = 1; c.tile_off = 0; c.width = 256; c.n_w = 3; c.n_valid = n_pad;
+        float* cpart = (float*)(sc + L.cs_part);
+        c.wsum_partial = cpart + (size_t)3 * 2 * L.dw_splits * 256;
         for (int k = 0; k < 3; ++k) {
-            j.row_weight[k] = P.dz2 + (size_t)k * n_pad;
-            j.partial[k] = cpart;
+            c.w[k] = P.dz2 + (size_t)k * n_pad;
+            c.partial[k] = cpart + (size_t)k * 2 * L.dw_splits * 256;
             ReduceJob& r = R.jobs[R.n_jobs++];
-            r.partial = cpart; r.splits = L.cs_splits; r.rows = 1; r.nw = 256;
+            r.partial = c.partial[k]; r.splits = 2 * L.dw_splits; r.rows = 1; r.nw = 256;
             r.dst = dW2 + k * 256; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = 0;
-            cpart += (size_t)L.cs_splits * 256;
+            ReduceJob& rs = R.jobs[R.n_jobs++];
+            rs.partial = c.wsum_partial + k; rs.splits = 2 * L.dw_splits; rs.rows = 1; rs.nw = 4;
+            rs.dst = db2 + k; rs.dst_pitch = 0; rs.out_rows = 1; rs.out_cols = 1; rs.factor = 1.f; rs.use_cot_scale = 0;
         }
     }
-    e = profiled(T_COLSUM, st, [&] { return launch_colsum(C, L.cs_splits, st); });
+    e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
     if (e != cudaSuccess) return (int)e;
-    e = profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
-    if (e != cudaSuccess) return (int)e;
-    for (int k = 0; k < 3; ++k) {
-        e = profiled(T_SUM, st, [&] { return launch_sum(P.dz2 + (size_t)k * n_pad, n_pad, (float*)(sc + L.sum_part) + 64 * k, db2 + k, st); });
-        if (e != cudaSuccess) return (int)e;
-    }
-    return 0;
+    return (int)profiled(T_REDUCE, st, [&] { return launch_reduce(R, st); });
 }
 
 

@@ -103,6 +103,20 @@ __device__ __forceinline__ void chain_teardown(const ChainSmem& s, uint32_t tmem
     if ((threadIdx.x >> 5) == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// Which tiles a (virtual) CTA owns: first, first + stride, ... (n of them).  Plain kernels: one CTA per blockIdx; the
+// fused backward (sdf_chain.cu) runs two virtual CTAs per block and gives every one its own map.
+struct TileMap {
+    int64_t first, stride;
+    int n;
+};
+__device__ __forceinline__ TileMap tilemap_grid(int n_tiles) {
+    TileMap m;
+    m.first = blockIdx.x;
+    m.stride = gridDim.x;
+    m.n = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    return m;
+}
+
 // warp 0, one lane
 __device__ __forceinline__ void chain_prefetch_step(const ChainTable& tab, int st, int64_t tile) {
 #pragma unroll
@@ -115,12 +129,12 @@ __device__ __forceinline__ void chain_prefetch_step(const ChainTable& tab, int s
     }
 }
 
-__device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTable& tab, const uint8_t* wblob, int n_my_tiles) {
+__device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTable& tab, const uint8_t* wblob, const TileMap tm) {
     uint32_t it = 0;
     unsigned long long* tab_trace = tab.trace; (void)tab_trace;
     const uint64_t keep = l2_policy_evict_last();
-    for (int t = 0; t < n_my_tiles; ++t) {
-        const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    for (int t = 0; t < tm.n; ++t) {
+        const int64_t tile = tm.first + (int64_t)t * tm.stride;
         for (int st = 0; st < tab.n_steps; ++st) {
             // The producer reaches step st's first weight slice while MMA(st-1) is still running, i.e. about one
             // epilogue + one MMA phase before epilogue(st) reads these streams: enough to cover DRAM latency, short
@@ -141,6 +155,11 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
             }
         }
     }
+}
+__device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTable& tab, const uint8_t* wblob, int n_my_tiles) {
+    TileMap tm = tilemap_grid(0);
+    tm.n = n_my_tiles;
+    chain_producer(s, tab, wblob, tm);
 }
 
 // warp 1, ALL lanes (convergent): the waits are warp-wide, one elected lane issues.  Compared with running the whole
@@ -185,42 +204,6 @@ __device__ __forceinline__ void chain_mma_warp(const ChainSmem& s, const ChainTa
             }
             if (elect_one()) umma_commit(s.acc_full);
             __syncwarp();
-        }
-    }
-}
-
-// warp 1, one lane
-__device__ __forceinline__ void chain_mma(const ChainSmem& s, const ChainTable& tab, uint32_t tmem, int n_my_tiles) {
-    uint32_t it = 0, sig = 0;
-    unsigned long long* tab_trace = tab.trace; (void)tab_trace;
-    const uint32_t a_base = smem_u32(s.sA);
-    const uint32_t ring_base = smem_u32(s.ring);
-    for (int t = 0; t < n_my_tiles; ++t) {
-        for (int st = 0; st < tab.n_steps; ++st, ++sig) {
-            const uint32_t n = tab.steps[st].n;
-            const uint32_t idesc = umma_idesc(TILE_M, n, FMT_F16, FMT_F16);
-            const int nsl = tab.steps[st].k / SLICE_K;
-            RNB_TR(2, sig, 0, true);
-            mbar_wait(s.a_ready, sig & 1);
-            RNB_TR(2, sig, 1, true);
-            tc_fence_after();
-            for (int ks = 0; ks < nsl; ++ks, ++it) {
-                const uint32_t slot = it % RING_STAGES, ph = (it / RING_STAGES) & 1;
-                RNB_TR(1, it, 0, true);
-                mbar_wait(&s.full[slot], ph);
-                RNB_TR(1, it, 1, true);
-                tc_fence_after();
-#pragma unroll
-                for (int j = 0; j < SLICE_K / 16; ++j) {
-                    const uint64_t ad = umma_desc(a_base + (uint32_t)(ks * (SLICE_K / 16) + j) * (2 * TILE_M * 16), TILE_M * 16, 128);
-                    const uint64_t bd = umma_desc(ring_base + slot * STAGE_BYTES + (uint32_t)j * (2 * n * 16), n * 16, 128);
-                    umma_f16(tmem, ad, bd, idesc, ((ks | j) != 0) || tab.steps[st].accumulate);
-                }
-                umma_commit(&s.empty[slot]);
-                RNB_TR(1, it, 2, true);
-            }
-            umma_commit(s.acc_full);
-            RNB_TR(2, sig, 2, true);
         }
     }
 }
@@ -321,18 +304,23 @@ struct Epi {
     int row;             // 0..127 = TMEM lane = point row inside the tile
     int half;            // 0: accumulator columns 0..127, 1: columns 128..255 (warp-uniform)
     int col0;            // = half * 128
+    int bar_id;          // named barrier of this (virtual) CTA's 256 epilogue threads
 
-    __device__ __forceinline__ void init(const ChainSmem& s, uint32_t tmem) {
+    // local_warp: warp index inside the (virtual) CTA, 2..9 for epilogue warps; the TMEM lane quadrant follows the
+    // hardware warp id (threadIdx.x >> 5) & 3 -- each group of four consecutive epilogue warps covers all four.
+    __device__ __forceinline__ void init(const ChainSmem& s, uint32_t tmem, int local_warp = -1, int barrier_id = 1) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int quad = warp & 3;           // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        if (local_warp < 0) local_warp = warp;
         sA = s.sA;
         acc_full = s.acc_full;
         a_ready = s.a_ready;
         tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
         row = quad * 32 + lane;
-        half = (warp - 2) >> 2;
+        half = (local_warp - 2) >> 2;
         col0 = half * EPI_HALF_COLS;
         acc_cnt = 0;
+        bar_id = barrier_id;
         tab_trace = nullptr;
     }
     unsigned long long* tab_trace;
@@ -350,8 +338,8 @@ struct Epi {
         RNB_TR(3, acc_cnt, 2, threadIdx.x == 64);
         mbar_arrive(a_ready);
     }
-    // rendezvous of the 256 epilogue threads (named barrier 1; warps 0/1 never join)
-    __device__ __forceinline__ void sync_epi() const { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+    // rendezvous of the 256 epilogue threads (named barrier bar_id; the producer / MMA warps never join)
+    __device__ __forceinline__ void sync_epi() const { asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory"); }
     __device__ __forceinline__ void st_a(int chunk, uint4 v) const {
         *reinterpret_cast<uint4*>(sA + ((size_t)chunk * TILE_M + row) * 16) = v;
     }

@@ -4,19 +4,40 @@
 
 namespace rnb {
 
-constexpr int DW_MAX_JOBS = 16;
+constexpr int DW_MAX_JOBS = 10;
 constexpr int RED_MAX_JOBS = 40;
+constexpr int DW_MAX_PAIRS = 3;
+constexpr int DW_MAX_CS = 3;
 
+// Column sums taken from a staged tile by the warps that are idle while the MMAs run: bias gradients (unweighted sum of an
+// A-side cotangent tile) and the rank-1..3 weight gradients that used to need their own pass over a stream
+// (SDF: dW_8[0,:] = sum_p uabar_7[p,:] + sum_p d_sdf[p] a_7[p,:];  albedo: dW_2[k,:] = sum_p dz2[k,p] h_1[p,:]).
+struct DwColsum {
+    int pair;                 // stage pair whose tile is summed
+    int tile_off;             // byte offset of the summed tile inside the stage: 0 = A side, 32768 = B side, above = rider
+    int width;                // columns of that tile (256, nw, or 128 for a rider half)
+    int col0;                 // first output column (a rider half covers columns col0 .. col0 + 127 of the sum)
+    int n_w;                  // 0: one unweighted sum -> partial[0];  1..3: that many weighted sums over the same tile
+    const float* w[3];        // per-point weights (fp32, indexed by point); points >= n_valid weigh 0
+    int64_t n_valid;
+    float* partial[3];        // each [splits][256] fp32
+    float* wsum_partial;      // optional [splits][4]: the sums of the weights themselves (db of a 1..3-row layer)
+};
 struct DwJob {
-    const uint8_t* a[2];      // A-side streams, 256 columns wide (M = 256 output rows of dW)
-    const uint8_t* b[2];      // B-side streams
-    int b_chunks[2];          // total 8-column chunks of each B stream (8, 32 or 40)
+    const uint8_t* a[DW_MAX_PAIRS];      // A-side streams, 256 columns wide (M = 256 output rows of dW)
+    const uint8_t* b[DW_MAX_PAIRS];      // B-side streams (unused for pairs >= mma_pairs)
+    int b_chunks[DW_MAX_PAIRS];          // total 8-column chunks of each B stream (8, 32 or 40)
+    // "rider": 128 columns (16 KB per sub-tile) of a 256-wide stream that is only column-summed, carried in the unused
+    // part of a narrow job's B slot (nw = 64 leaves 24 KB) so that it costs no ring stage of its own; null = none
+    const uint8_t* x[DW_MAX_PAIRS];
+    int x_chunk0[DW_MAX_PAIRS];          // first 8-column chunk of the rider window (0 or 16)
     int b_chunk0;             // first chunk of the B column window
-    int n_pairs;
+    int n_pairs;              // stages per 64-point sub-tile
+    int mma_pairs;            // pairs [0, mma_pairs) are contracted; the rest only stage their A tile for column sums
     int nw;                   // window width N (multiple of 16, <= 256)
     float* partial;           // [splits][256][nw] fp32
-    int colsum_pair;          // pair whose A-side tile is also column-summed (bias gradient), -1 = none
-    float* cs_partial;        // [splits][256] fp32
+    int n_cs;
+    DwColsum cs[DW_MAX_CS];
 };
 struct DwParams {
     int n_jobs;
@@ -24,20 +45,9 @@ struct DwParams {
     DwJob jobs[DW_MAX_JOBS];
 };
 
-struct ColsumJob {
-    const uint8_t* stream;
-    int chunks;               // stream width / 8
-    int n_w;                  // 1..3 weighted sums taken in ONE pass over the stream
-    const float* row_weight[3];   // optional per-point weights (fp32 [n_pts]); null = 1
-    float* partial[3];            // each [splits][chunks*8]
-};
-struct ColsumParams {
-    int n_jobs;
-    int n_sub;
-    int64_t n_pts;
-    ColsumJob jobs[DW_MAX_JOBS * 2];
-};
-
+// fused backward (sdf_chain.cu, sdf_bwd_fused_kernel): K3a parameters + one weight-gradient job per layer + the hand-over
+// queues.  job.partial / job.cs_partial are indexed by the worker's replica index instead of a split index.
+constexpr int FUSED_MAX_WORKERS = 160;
 struct ReduceJob {
     const float* partial;     // [splits][rows][nw]
     int splits, rows, nw;

@@ -69,7 +69,25 @@ struct SdfBwdParams {
     uint8_t* st_zbar;          // 8 streams, zbar_l (scaled)
     uint8_t* st_dfeat;         // 1 stream, d_feat (scaled)
     size_t stream_stride;
+    int keep_streams;          // store uin / zbar with the default L2 policy instead of evict-first (fused launch: read back soon)
     int thread_prefetch;       // epilogue threads hint the next step's stream chunks into L2 (prefetch.global.L2)
 };
 
+}  // namespace rnb
+
+#include "dw_params.h"
+namespace rnb {
+struct SdfBwdFusedParams {
+    SdfBwdParams chain;
+    DwJob jobs[9];                            // job l: dW_l (l = 8: the feature rows of W_8)
+    int n_dw;                                 // blocks [0, n_dw) are weight-gradient workers
+    uint8_t dw_layer[FUSED_MAX_WORKERS];      // layer of worker j
+    uint8_t dw_replica[FUSED_MAX_WORKERS];    // its index among the workers of that layer (partial slot)
+    int* q;                                   // [9][n_tiles] tile indices in completion order, -1 = not yet published
+    int* q_tail;                              // [9] entries published
+    int* q_head;                              // [9] tickets taken
+    int* q_cnt;                               // [n_tiles][9] epilogue warps done with (tile, layer), zeroed before launch
+    int stagger_ns;                           // spread of the chain CTAs' start times (0 = none)
+    unsigned long long* dbg;                  // optional [2][FUSED_MAX_WORKERS]: block end / start times (globaltimer ns)
+};
 }  // namespace rnb

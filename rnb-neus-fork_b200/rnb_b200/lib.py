@@ -82,6 +82,7 @@ _SIGNATURES = {
     "rnb_sdf_fwd": (C.c_int, [C.POINTER(Points), _VP, _VP, _VP, C.c_float, _VP]),
     "rnb_sdf_fwd_grad": (C.c_int, [C.POINTER(Points)] + [_VP] * 10),
     "rnb_sdf_bwd_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "rnb_sdf_bwd_debug_offset": (C.c_size_t, [C.c_int64]),
     "rnb_albedo_wblob_bytes": (C.c_size_t, []),
     "rnb_albedo_aux_floats": (C.c_size_t, []),
     "rnb_albedo_pack": (C.c_int, [_VP] * 9),
