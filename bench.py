@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the RNb-NeuS hot path on B200 (contract: see the task prompt / DESIGN.md 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dp8192|b512_noalbedo|grid512] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dp8192|b512|b512_noalbedo|womask_b512|render_bg|grid512|perray]
+                    [--impl reference] [--no-extras]
 
-A "step" is one pass of the train_rnb hot path over one synthetic ray batch: render_rnb_warmup forward + the loss of
-exp_runner.py:241-256 + backward (eikonal double-backward included) + the gradient all-reduce when N > 1.
-Default workload (BASELINE.json configs[3]): wmask_rnb.conf with the albedo network, 8192 rays per GPU, weak scaling.
-Prints ONE JSON line on rank 0.
+A "step" is one train_rnb iteration over one synthetic ray batch: render_rnb_warmup forward + the loss of
+exp_runner.py:241-256 + backward (eikonal double-backward included) + the gradient all-reduce when N > 1 + the Adam
+update (exp_runner.py:259-263).  Default workload (BASELINE.json configs[3]): wmask_rnb.conf with the albedo network,
+8192 rays per GPU, weak scaling.  The default line also carries the second half of BASELINE.json's metric
+("grid512": this rank's x-slab of the 512^3 SDF lattice, configs[4]), the per-ray kernels at a streaming size ("perray"),
+the reference on the same GPU through PyTorch-CUDA ("cuda_reference"), the CPU arm ("cpu_baseline") and, under torchrun,
+a data-parallel equivalence check ("dp_check").  Prints ONE JSON line on rank 0.
 """
 import argparse
 import datetime
@@ -45,14 +49,46 @@ BYTES_PER_POINT = {
     "albedo_fwd": 512 + 128 + 512 + 512 + 36,
     "albedo_bwd": 2 * 512 + 3 * 512 + 40,
 }
-# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per point of the same launches (profiles/)
-NCU_DRAM_BYTES_PER_POINT = {"sdf_fwd_grad": 11747, "sdf_bwd_data": 25622}     # profiles/r01_ncu_summary_s4.md, 1 048 576 points
+
+
+def source_sha():
+    """Hash of the kernel sources this build was made from.  profiles/r02_traffic.json (written by
+    profiles/summarize_ncu.py --traffic from an `ncu --set full` capture) carries the hash of the sources it was measured
+    on; `roofline.traffic` is printed only when the two agree, so a stale figure can never ride along a changed kernel."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "rnb-neus-fork_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic():
+    """-> ({kernel: dram bytes per point}, note)"""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.isfile(p):
+        return {}, "no ncu capture committed for this build"
+    d = json.load(open(p))
+    if d.get("source_sha") != source_sha():
+        return {}, f"profiles/r02_traffic.json was captured on sources {d.get('source_sha')}, this build is {source_sha()}"
+    return {k: v["dram_bytes_per_point"] for k, v in d["kernels"].items()}, f"profiles/r02_traffic.json ({d.get('capture')})"
+
 
 WORKLOADS = {
     "dp8192": dict(rays=8192, no_albedo=False, desc="wmask_rnb.conf train_rnb (render_rnb_warmup fwd + loss + bwd + eikonal), "
                    "8192 rays/GPU, 64+64 samples, 3 lights, albedo net on"),
     "b512_noalbedo": dict(rays=512, no_albedo=True, desc="wmask_rnb_noalbedo.conf train_rnb --no_albedo, 512 rays, 64+64 samples"),
     "b512": dict(rays=512, no_albedo=False, desc="wmask_rnb.conf train_rnb, 512 rays, 64+64 samples"),
+    "womask_b512": dict(rays=512, no_albedo=False, womask=True,
+                        desc="womask_rnb.conf train_rnb as shipped (confs/womask_rnb.conf:28,37,85: n_outside = 0, mask_weight = 0 "
+                             "so the mask is all ones, cos_anneal_ratio = iter/50000 < 1, render_rnb after the warm-up), 512 rays. "
+                             "render_rnb* with n_outside > 0 has no reference (the reference's own call raises, SURVEY fact 5) "
+                             "and is not provided"),
+    "render_bg": dict(rays=512, no_albedo=False, render_bg=True,
+                      desc="NeuSRenderer.render() with the NeRF++ background field, n_outside = 32 (models/renderer.py:556-648), "
+                           "forward only like its one reference caller (render_novel_image), 512 rays x (128 + 32) samples"),
     "grid512": dict(rays=0, no_albedo=True, desc="validate_mesh extract_fields, 512^3 SDF lattice sharded in x-slabs"),
     "perray": dict(rays=131072, no_albedo=False, desc="compositing + hierarchical-sampling kernels alone at 131072 rays "
                    "(HBM-bound per-ray kernels, SURVEY 8d algorithmic bytes)"),
@@ -68,7 +104,7 @@ def peaks():
 
 
 def loss_fn(out, true_rgb, mask, igr_weight=0.1, mask_weight=0.1):
-    """reference exp_runner.py:241-256"""
+    """reference exp_runner.py:241-256 (mask_weight = 0 in womask_rnb.conf: the BCE term drops out)"""
     mask_sum = mask.sum() + 1e-5
     err = ((out["color_fine"] - true_rgb) * mask[None, :, :]).reshape(-1, 3)
     color_loss = F.l1_loss(err, torch.zeros_like(err), reduction="sum") / (mask_sum * true_rgb.shape[0])
@@ -318,6 +354,179 @@ def cpu_baseline(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+class Ctx:
+    """Process-wide handles of one bench run."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.args = args
+        self.pk = peaks()
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K steps between barrier + synchronize on both sides, CUDA events on the launch stream, MAX over ranks."""
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+
+def grid512_section(cx, sdf, steps=3, warmup=1):
+    """BASELINE.json configs[4]: this rank's x-slab of the 512^3 lattice (models/renderer.py:10-25, 1219-1224).
+    value = whole-lattice queries / slowest rank's time; e2e adds the D2H copy of the slab into pinned host memory."""
+    from rnb_b200 import grid, lib as L
+    R = 512
+    x0, x1 = grid.slab_bounds(R, cx.rank, cx.world)
+    out = torch.empty(x1 - x0, R, R, dtype=torch.float32, device=cx.dev)
+    host = torch.empty(x1 - x0, R, R, dtype=torch.float32).pin_memory()
+    bmin, bmax = [-1.01] * 3, [1.01] * 3
+    step = lambda i: grid.sdf_slab(sdf, bmin, bmax, R, x0, x1, out=out)
+    for i in range(warmup):
+        step(i)
+    L.profile_enable(True)
+    n0 = L.launch_count()
+    ms = cx.timed(step, steps)
+    launches = L.launch_count() - n0
+    prof = L.profile_collect()
+    L.profile_enable(False)
+
+    def e2e_step(i):
+        step(i)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = cx.timed(e2e_step, 2)
+    n_launch = (x1 - x0) * R * R
+    k_ms = prof["sdf_fwd"][0] / prof["sdf_fwd"][1]
+    tf = FLOP_SDF_ONLY * n_launch / k_ms / 1e9
+    return dict(metric="mesh SDF queries/s", value=R ** 3 / ms * 1e3, unit="SDF queries/s", ms_per_step=ms, steps=steps,
+                warmup=warmup, scaling="strong", gpu_launches=int(launches),
+                config=dict(workload=WORKLOADS["grid512"]["desc"], slab=f"x in [{x0},{x1}) of {R}", parallelism=f"slab{cx.world}",
+                            l2="no activation streams: the kernel reads 2 MB of packed weights (L2-resident) and writes 4 B per "
+                               "query; the slab output (>= 64 MiB) is larger than L2"),
+                e2e=dict(value=R ** 3 / ms_e2e * 1e3, unit="SDF queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=n_launch * 4,
+                         ms_per_step=ms_e2e),
+                roofline=dict(bound="tensor", kernel="sdf_fwd", achieved=tf, peak=cx.pk["tf_sustained"], unit="TFLOP/s",
+                              frac=tf / cx.pk["tf_sustained"], frac_of_burst_peak=tf / cx.pk["tf_burst"],
+                              algorithmic_flop_per_query=FLOP_SDF_ONLY, queries_per_launch=n_launch, ms_per_launch=k_ms,
+                              hbm_frac=4.0 * n_launch / k_ms / 1e6 / cx.pk["hbm"], traffic=None,
+                              peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({cx.pk['src']})"))
+
+
+def perray_section(cx, B=131072):
+    """K5 / K6 at a ray count where they stream (the 8192-ray launches of the train step are single waves)."""
+    import io
+    import contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        run_perray(cx.args, dict(WORKLOADS["perray"], rays=B))
+    d = json.loads(buf.getvalue().strip().splitlines()[-1])
+    return dict(rays=B, kernels=d["kernels"], roofline=d["roofline"], config=d["config"])
+
+
+def cuda_reference_section(cx, sizes=(512, 2048), steps=3):
+    """The reference's own implementation through PyTorch-CUDA (ATen + cuBLAS + autograd, fp32, TF32 off) on the same GPU:
+    the unmodified reference when its tree is staged (oracle/stage_reference.py -> baseline/_ref, or /root/reference),
+    else oracle/torch_port.py.  A GPU-vs-GPU baseline next to the CPU one ("optional second baseline")."""
+    from oracle import ref_loader
+    from rnb_b200 import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    kind = "reference" if ref_loader.available() else "port"
+    res = dict(kind=kind, dtype="f32 (allow_tf32 = False)", steps=steps, sizes={})
+    try:
+        if kind == "reference":
+            from oracle.gen_golden import build_reference_nets, loss_fn as ref_loss
+            ref, nerf, sdf, var, col = build_reference_nets(False)
+            for m in (nerf, sdf, var, col):
+                m.to(cx.dev)
+            renderer = ref.renderer.NeuSRenderer(nerf, sdf, var, col, **synth.WMASK_CONF["neus_renderer"])
+            renderer.color_depth = 3
+        else:
+            from oracle import torch_port as T
+            _, sdf, var, col = build("cpu")
+            leaf = lambda m: {k: v.detach().clone().to(cx.dev).requires_grad_(True) for k, v in m.state_dict().items()}
+            sdf_sd, col_sd = leaf(sdf), leaf(col)
+            variance = var.variance.detach().clone().to(cx.dev).requires_grad_(True)
+        for B in sizes:
+            b = {k: v.to(cx.dev) for k, v in synth.make_batch(B, 3, True, 1).items()}
+
+            def step(i):
+                with torch.device(cx.dev):         # the reference builds its temporaries with bare factory calls
+                    if kind == "reference":
+                        for m in (sdf, var, col):
+                            m.zero_grad()
+                        out = renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
+                                                         cos_anneal_ratio=1.0, no_albedo=False)
+                        ref_loss(out, b["true_rgb"], b["mask"], 0.1, 0.1, 3)[0].backward()
+                    else:
+                        for t in list(sdf_sd.values()) + list(col_sd.values()) + [variance]:
+                            t.grad = None
+                        out = T.render_rnb(sdf_sd, col_sd, variance, b["rays_o"], b["rays_d"], b["near"], b["far"],
+                                           b["lights_dir"], b["t_rand"], 1.0, True, False)
+                        T.loss_fn(out, b["true_rgb"], b["mask"]).backward()
+            step(0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res["sizes"][str(B)] = dict(ms_per_step=ms, rays_per_s=B / ms * 1e3,
+                                        peak_mem_gb=torch.cuda.max_memory_allocated(cx.dev) / 2 ** 30)
+        res["value"] = max(v["rays_per_s"] for v in res["sizes"].values())
+        res["unit"] = "rays/s"
+    except Exception as e:  # noqa: BLE001  (a baseline that cannot run must not take the bench line down with it)
+        res["error"] = f"{type(e).__name__}: {e}"[:300]
+    torch.cuda.empty_cache()
+    return res
+
+
+def dp_check(cx, train_step, red, batches):
+    """Data-parallel equivalence with the real kernels under NCCL (reference seam exp_runner.py:170, 194):
+    one untimed step -- every rank keeps its pre-reduction flat gradient, all ranks gather them, and the all-reduced
+    buffer must equal their mean in the rank order NCCL is NOT obliged to use, so the comparison is to fp32 rounding of a
+    sum of `world` terms (bit-exact for world = 2); the ranks must also have drawn different rays."""
+    dist = cx.dist
+    b = batches[0]
+    train_step(b, reduce=False)
+    local = red.collect().clone()
+    gathered = [torch.empty_like(local) for _ in range(cx.world)]
+    dist.all_gather(gathered, local)
+    red.all_reduce()
+    mean = torch.stack(gathered).double().mean(0)
+    got = red.flat.double()
+    err = float((got - mean).norm() / mean.norm().clamp_min(1e-300))
+    rays = [torch.empty_like(b["rays_d"]) for _ in range(cx.world)]
+    dist.all_gather(rays, b["rays_d"].contiguous())
+    distinct = all(not torch.equal(rays[0], r) for r in rays[1:])
+    differ = float((gathered[0] - gathered[-1]).norm() / gathered[0].norm().clamp_min(1e-30))
+    ok = err < 1e-6 and distinct and differ > 1e-3
+    return dict(status="ok" if ok else "FAILED", allreduce_vs_mean_of_ranks_rel_l2=err, ranks_drew_distinct_rays=distinct,
+                rank_gradients_differ_rel_l2=differ, flat_buffer_bytes=red.nbytes)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,6 +535,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dp8192", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="train line only: skip grid512 / perray / cuda_reference")
     ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (rnb_b200.graph_step)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -340,198 +550,183 @@ def main():
             run_perray(args, wl)
         return
 
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from rnb_b200 import synth, lib as L, grid
+    cx = Ctx(args)
+    dist, world, rank, dev, pk = cx.dist, cx.world, cx.rank, cx.dev, cx.pk
+    from rnb_b200 import synth, lib as L
     from rnb_b200.parallel import FlatGradAllReducer
     from rnb_b200.optim import FlatAdam
 
     renderer, sdf, var, col = build(dev)
-    pk = peaks()
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps
 
     if args.workload == "grid512":
-        R = 512
-        x0, x1 = grid.slab_bounds(R, rank, world)
-        out = torch.empty(x1 - x0, R, R, dtype=torch.float32, device=dev)
-        bmin, bmax = [-1.01] * 3, [1.01] * 3
-        host = torch.empty(x1 - x0, R, R, dtype=torch.float32).pin_memory()
-        step = lambda i: grid.sdf_slab(sdf, bmin, bmax, R, x0, x1, out=out)
-        clk = ClockSampler(local)
-        for i in range(args.warmup):
-            step(i)
-        L.profile_enable(True)
-        n0 = L.launch_count()
-        sync_all()
+        clk = ClockSampler(cx.local)
         clk.mark_start()
-        ms = timed(step, args.steps)
+        sec = grid512_section(cx, sdf, steps=max(3, args.steps), warmup=args.warmup)
         clk.mark_end()
-        launches = L.launch_count() - n0
-        prof = L.profile_collect()
-        L.profile_enable(False)
-        clocks = clk.stop()
+        line = dict(sec, n_gpus=world, higher_is_better=True, vs_baseline=None, dtype="f16 operands / f32 accumulate",
+                    data="synthetic", clocks=clk.stop())
+        if rank == 0:
+            if world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(args, wl)
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-        def e2e_step(i):
-            step(i)
-            host.copy_(out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        ms_e2e = timed(e2e_step, max(2, args.steps // 4))
-        units = R ** 3
-        kname, flop_unit, units_launch = "sdf_fwd", FLOP_SDF_ONLY, (x1 - x0) * R * R
-        h2d, d2h = 0, (x1 - x0) * R * R * 4
-        unit = "SDF queries/s"
-    else:
-        B = wl["rays"]
-        no_albedo = wl["no_albedo"]
-        params = list(sdf.parameters()) + list(var.parameters()) + ([] if no_albedo else list(col.parameters()))
-        red = FlatGradAllReducer(params)
-        opt = FlatAdam(params, lr=5e-4, reducer=red)   # one launch over the flat buffers the all-reduce uses
-        host_b = [{k: v.pin_memory() for k, v in synth.make_batch(B, 3, True, 1 + rank, view=i).items()} for i in range(4)]
-        dev_b = [{k: v.to(dev) for k, v in hb.items()} for hb in host_b]
-        keys = ("rays_o", "rays_d", "near", "far", "lights_dir", "true_rgb", "mask")
+    B = wl["rays"]
+    no_albedo = wl["no_albedo"]
+    womask = bool(wl.get("womask"))
+    render_bg = bool(wl.get("render_bg"))
+    warm = not womask
+    if render_bg:
+        renderer.n_outside = 32
+    params = list(sdf.parameters()) + list(var.parameters()) + ([] if no_albedo else list(col.parameters()))
+    red = FlatGradAllReducer(params)
+    opt = FlatAdam(params, lr=5e-4, reducer=red)   # one launch over the flat buffers the all-reduce uses
+    host_b = [{k: v.pin_memory() for k, v in synth.make_batch(B, 3, warm, 1 + rank, view=i).items()} for i in range(4)]
+    if womask:       # mask_weight = 0 -> mask = ones (exp_runner.py:187-194)
+        for hb in host_b:
+            hb["mask"].fill_(1.0)
+    dev_b = [{k: v.to(dev) for k, v in hb.items()} for hb in host_b]
+    keys = ("rays_o", "rays_d", "near", "far", "lights_dir", "true_rgb", "mask")
+    anneal = 0.3 if womask else 1.0
+    mask_w = 0.0 if womask else 0.1
 
-        def train(b):
-            # every step starts from weights an optimiser would have just updated: bump the version counters so that nothing
-            # keyed on them (the cached packed weights of the no_grad sampling pass) carries over from the previous step
-            torch.autograd.graph.increment_version(params)
-            red.zero()
-            out = renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"],
-                                             cos_anneal_ratio=1.0, no_albedo=no_albedo)
-            loss = loss_fn(out, b["true_rgb"], b["mask"])
-            loss.backward()
+    def fwd_bwd(b, reduce=True):
+        # every step starts from weights an optimiser has just updated: bump the version counters so that nothing
+        # keyed on them (the cached packed weights of the no_grad sampling pass) carries over from the previous step
+        torch.autograd.graph.increment_version(params)
+        red.zero()
+        fn = renderer.render_rnb_warmup if warm else renderer.render_rnb
+        out = fn(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"], cos_anneal_ratio=anneal, no_albedo=no_albedo)
+        loss = loss_fn(out, b["true_rgb"], b["mask"], mask_weight=mask_w)
+        loss.backward()
+        if reduce:
             red.all_reduce()
+        return loss
+
+    if render_bg:
+        def fwd_bwd(b, reduce=True):      # noqa: F811  forward only: render() has no training caller upstream
+            with torch.no_grad():
+                out = renderer.render(b["rays_o"], b["rays_d"], b["near"], b["far"], cos_anneal_ratio=1.0)
+            return out["color_fine"].sum()
+    if args.graph:
+        from rnb_b200.graph_step import GraphedTrainStep
+        gs = GraphedTrainStep(renderer, params, lambda o, rgb, m: loss_fn(o, rgb, m, mask_weight=mask_w), dev_b[0], warmup=warm,
+                              no_albedo=no_albedo, reducer=red)
+
+        def fwd_bwd(b, reduce=True):       # noqa: F811  (same contract: grads in the flat buffer, all-reduce outside the graph)
+            loss = gs(b)
+            if reduce:
+                red.all_reduce()
             return loss
 
-        step = lambda i: train(dev_b[i % 4])
-        if args.graph:
-            from rnb_b200.graph_step import GraphedTrainStep
-            gs = GraphedTrainStep(renderer, params, lambda o, rgb, m: loss_fn(o, rgb, m), dev_b[0], warmup=True,
-                                  no_albedo=no_albedo, reducer=red)
-
-            def train(b):       # noqa: F811  (same contract: grads in the flat buffer, all-reduce outside the graph)
-                loss = gs(b)
-                red.all_reduce()
-                return loss
-            step = lambda i: train(dev_b[i % 4])
-        clk = ClockSampler(local)
-        for i in range(args.warmup):
-            step(i)
-        L.profile_enable(True)
-        n0 = L.launch_count()
-        sync_all()
-        clk.mark_start()
-        ms = timed(step, args.steps)
-        clk.mark_end()
-        launches = L.launch_count() - n0
-        if args.graph:      # replays issue no calls through the C-ABI: count the library kernels captured in the graph
-            launches += gs.launches_per_replay * args.steps
-        prof = L.profile_collect()
-        L.profile_enable(False)
-        clocks = clk.stop()
-
-        def e2e_step(i):
-            hb = host_b[i % 4]
-            b = {k: hb[k].to(dev, non_blocking=True) for k in keys}
-            loss = train(b)
-            return float(loss.detach())              # device -> host read of the step's result
-        ms_e2e = timed(e2e_step, args.steps)
-
-        def full_step(i):
-            step(i)
+    def train(b):
+        """one train_rnb iteration: forward + loss + backward (+ all-reduce) + Adam (exp_runner.py:222-263)"""
+        loss = fwd_bwd(b)
+        if not render_bg:
             opt.step()
-        full_step(0)
-        ms_full = timed(full_step, max(3, args.steps // 2))
-        units = B * world
-        h2d = sum(host_b[0][k].numel() * 4 for k in keys)
-        d2h = 4
-        unit = "rays/s"
+        return loss
 
+    step = lambda i: train(dev_b[i % 4])
+    clk = ClockSampler(cx.local)
+    for i in range(args.warmup):
+        step(i)
+    check = dp_check(cx, fwd_bwd, red, dev_b) if (world > 1 and not render_bg) else None
+    L.profile_enable(True)
+    n0 = L.launch_count()
+    cx.sync_all()
+    clk.mark_start()
+    ms = cx.timed(step, args.steps)
+    clk.mark_end()
+    launches = L.launch_count() - n0
+    if args.graph:      # replays issue no calls through the C-ABI: count the library kernels captured in the graph
+        launches += gs.launches_per_replay * args.steps
+    prof = L.profile_collect()
+    L.profile_enable(False)
+    clocks = clk.stop()
+
+    def e2e_step(i):
+        hb = host_b[i % 4]
+        b = {k: hb[k].to(dev, non_blocking=True) for k in keys}
+        loss = train(b)
+        return float(loss.detach())              # device -> host read of the step's result
+    ms_e2e = cx.timed(e2e_step, args.steps)
+    ms_fwd_bwd = cx.timed(lambda i: fwd_bwd(dev_b[i % 4]), max(3, args.steps // 2))
+    units = B * world
+    h2d = sum(host_b[0][k].numel() * 4 for k in keys)
     value = units / ms * 1e3
-    e2e_val = units / ms_e2e * 1e3
-    # ---- roofline of the dominant tensor-core kernel, from the cudaEvent brackets recorded inside the timed region
+
+    # ---- per-kernel device times (cudaEvent brackets recorded by the library inside the timed region) and rooflines
+    nf, nc = B * 128, B * 112
+    flops = {"sdf_fwd_grad": (FLOP_FWD_FULL + FLOP_DX) * nf, "sdf_bwd_data": FLOP_BWD_DATA * nf,
+             "sdf_bwd_fused": (FLOP_BWD_DATA + FLOP_BWD_DW) * nf, "albedo_fwd": FLOP_ALB_FWD * nf, "albedo_bwd": 2 * 145664 * nf}
+    # dw_gemm launches: one for the SDF net, one for the albedo net per step
+    flops["dw_gemm"] = (FLOP_BWD_DW * nf + (0 if no_albedo else 2 * 145664 * nf)) / (1 if no_albedo else 2)
+    traffic_pp, traffic_note = ncu_traffic()
     kernels = {}
-    if args.workload == "grid512":
-        flops = {"sdf_fwd": FLOP_SDF_ONLY * units_launch}
-    else:
-        nf, nc = B * 128, B * 112
-        flops = {"sdf_fwd_grad": (FLOP_FWD_FULL + FLOP_DX) * nf, "sdf_bwd_data": FLOP_BWD_DATA * nf,
-                 "albedo_fwd": FLOP_ALB_FWD * nf, "albedo_bwd": 2 * 145664 * nf}
-        # dw_gemm launches: one for the SDF net, one for the albedo net per step
-        flops["dw_gemm"] = (FLOP_BWD_DW * nf + (0 if no_albedo else 2 * 145664 * nf)) / (1 if no_albedo else 2)
     for name, (tot, cnt) in prof.items():
         d = dict(ms_per_launch=tot / cnt, launches_per_step=cnt / args.steps, share_of_step=tot / (ms * args.steps))
-        if name in flops:
-            if name == "sdf_fwd" and args.workload != "grid512":
-                d["tflops"] = FLOP_SDF_ONLY * (B * 112) / (tot / args.steps) / 1e9
-            else:
-                d["tflops"] = flops[name] / (tot / cnt) / 1e9
+        if name in flops or name == "sdf_fwd":
+            fl = FLOP_SDF_ONLY * nc / (cnt / args.steps) if name == "sdf_fwd" else flops[name]
+            d["tflops"] = fl / (tot / cnt) / 1e9
             d["frac_of_tensor_peak"] = d["tflops"] / pk["tf_sustained"]
-        if args.workload != "grid512" and name in BYTES_PER_POINT:
-            nbytes = BYTES_PER_POINT[name] * B * 128
-            if name == "dw_gemm":       # two launches per step (SDF net, albedo net): report the SDF one's bytes on the mean
-                nbytes = (BYTES_PER_POINT[name] + (0 if no_albedo else 2816)) * B * 128 / (1 if no_albedo else 2)
+        if name in BYTES_PER_POINT:
+            nbytes = BYTES_PER_POINT[name] * nf
+            if name == "dw_gemm":       # two launches per step (SDF net, albedo net): the mean launch
+                nbytes = (BYTES_PER_POINT[name] + (0 if no_albedo else 2816)) * nf / (1 if no_albedo else 2)
+            d["algorithmic_bytes"] = nbytes
             d["gbs"] = nbytes / (tot / cnt) / 1e6
             d["frac_of_hbm_peak"] = d["gbs"] / pk["hbm"]
+        if name in traffic_pp:
+            d["ncu_dram_bytes"] = traffic_pp[name] * nf
         kernels[name] = d
     cand = [k for k in kernels if "tflops" in kernels[k]]
     top = max(cand, key=lambda k: kernels[k]["share_of_step"]) if cand else None
     roofline = None
     if top:
         k = kernels[top]
-        # the roofline that bounds the kernel is the one with the longer floor time
-        hbm_bound = "gbs" in k and k["frac_of_hbm_peak"] > k["frac_of_tensor_peak"]
-        pts_launch = (units_launch if args.workload == "grid512" else B * 128)
-        traffic = NCU_DRAM_BYTES_PER_POINT.get(top)
-        if hbm_bound:
-            roofline = dict(bound="hbm", kernel=top, achieved=k["gbs"], peak=pk["hbm"], unit="GB/s", frac=k["frac_of_hbm_peak"],
-                            traffic=traffic * pts_launch if traffic else None,
-                            peak_source=f"MEASURED_PEAKS.json hbm_gbs ({pk['src']})",
-                            tensor_frac=k["frac_of_tensor_peak"])
-        else:
-            roofline = dict(bound="tensor", kernel=top, achieved=k["tflops"], peak=pk["tf_sustained"], unit="TFLOP/s",
-                            frac=k["frac_of_tensor_peak"], traffic=traffic * pts_launch if traffic else None,
-                            peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})")
-    line = dict(metric=metric_name(args.workload), value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        # SURVEY 8(d): the MLP kernels are dense contractions, their algorithmic unit is FLOPs and the roof the (sustained)
+        # tensor peak.  What keeps this kernel under that roof is its HBM stream traffic: reported beside it.
+        roofline = dict(bound="tensor", kernel=top, achieved=k["tflops"], peak=pk["tf_sustained"], unit="TFLOP/s",
+                        frac=k["frac_of_tensor_peak"], frac_of_burst_peak=k["tflops"] / pk["tf_burst"],
+                        ms_per_launch=k["ms_per_launch"], points_per_launch=nf,
+                        algorithmic_flop_per_point=flops[top] / nf if top in flops else FLOP_SDF_ONLY,
+                        algorithmic_bytes=k.get("algorithmic_bytes"), hbm_frac=k.get("frac_of_hbm_peak"),
+                        traffic=k.get("ncu_dram_bytes"), traffic_source=traffic_note,
+                        peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})")
+    step_tf = (FLOP_PER_RAY[not no_albedo] * B / ms / 1e9) if not render_bg else None
+    line = dict(metric=metric_name(args.workload), value=value, unit="rays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate",
-                data="synthetic", config=dict(workload=wl["desc"] + (" [one CUDA graph per step]" if getattr(args, "graph", False) else ""),
-                                              weights="geometric init, torch.manual_seed(0)",
-                                              l2="per-step working set (activation streams, >1 GB) exceeds the 126 MB L2; "
-                                                 "4 input batches rotate", parallelism=f"dp{world}"),
-                clocks=clocks, e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                data="synthetic",
+                config=dict(workload=wl["desc"] + (" [one CUDA graph per step]" if args.graph else ""),
+                            step="forward + loss + backward + all-reduce + Adam (FlatAdam, one launch)" if not render_bg else "forward",
+                            weights="geometric init, torch.manual_seed(0)",
+                            l2="per-step working set (fp16 activation streams, > 1 GB at 8192 rays) exceeds the 126 MB L2; "
+                               "4 input batches rotate", parallelism=f"dp{world}"),
+                clocks=clocks, e2e=dict(value=units / ms_e2e * 1e3, unit="rays/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                                         ms_per_step=ms_e2e),
-                gpu_launches=int(launches), roofline=roofline, kernels=kernels)
-    if args.workload != "grid512":
-        line["full_step_with_adam_ms"] = ms_full
-        line["algorithmic_tflops"] = FLOP_PER_RAY[not no_albedo] * units / ms / 1e9 / world
+                gpu_launches=int(launches), roofline=roofline, kernels=kernels, fwd_bwd_ms=ms_fwd_bwd, source_sha=source_sha())
+    if step_tf is not None:
+        line["roofline_step"] = dict(bound="tensor", achieved=step_tf, peak=pk["tf_sustained"], unit="TFLOP/s",
+                                     frac=step_tf / pk["tf_sustained"], algorithmic_flop_per_ray=FLOP_PER_RAY[not no_albedo],
+                                     floor_ms_at_peak=FLOP_PER_RAY[not no_albedo] * B / pk["tf_sustained"] / 1e9)
+    if check is not None:
+        line["dp_check"] = check
+    extras = args.workload == "dp8192" and not args.no_extras and not args.graph
+    if extras:
+        line["grid512"] = grid512_section(cx, sdf)
+        if rank == 0:
+            line["perray"] = perray_section(cx)
+        cx.sync_all()
     if rank == 0:
+        if world == 1 and extras:
+            line["cuda_reference"] = cuda_reference_section(cx)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, wl)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

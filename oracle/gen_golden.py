@@ -191,6 +191,74 @@ def gen_render(name, warmup, no_albedo, B=16, perturb=True, r=1.0, mask_weight=0
     print(name, "loss", float(loss), "eik", float(out["gradient_error"]))
 
 
+LARGE_STRIDE = 16
+
+
+def gen_render_large(name, warmup, no_albedo, B=512, r=1.0, mask_weight=0.1, seed=21):
+    """BASELINE.json configs 0-2 size (512 rays, 65 536 fine points): the reference's outputs, loss and parameter
+    gradients (every LARGE_STRIDE-th element + the full per-tensor norms) AND the float64 oracle's gradients on the same
+    inputs and the reference's own sample depths -- so the GPU test at this size is pinned to the reference, and the
+    oracle is pinned to the reference at this size as well (tests/test_oracle_golden.py)."""
+    from oracle import rnb_oracle as O
+    ref, nerf, sdf, var, col = build_reference_nets(True)
+    renderer = ref.renderer.NeuSRenderer(nerf, sdf, var, col, **synth.WMASK_CONF["neus_renderer"])
+    renderer.color_depth = 3
+    b = synth.make_batch(B, 3, warmup, seed)
+    mask = b["mask"] if mask_weight > 0 else torch.ones_like(b["mask"])
+    fn = renderer.render_rnb_warmup if warmup else renderer.render_rnb
+    captured = {}
+    orig_core = renderer.render_core_mvps
+
+    def core(rays_o, rays_d, z_vals, *a, **k):
+        captured["z_vals"] = np32(z_vals)
+        return orig_core(rays_o, rays_d, z_vals, *a, **k)
+
+    renderer.render_core_mvps = core
+    for m in (sdf, var, col):
+        m.zero_grad()
+    with injected_rand([b["t_rand"] + 0.5]):
+        out = fn(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"], cos_anneal_ratio=r, no_albedo=no_albedo)
+    loss, closs, mloss = loss_fn(out, b["true_rgb"], mask, 0.1, mask_weight, 3)
+    loss.backward()
+    d = dict(B=np.array(B), seed=np.array(seed), t_rand=np32(b["t_rand"]), mask_used=np32(mask), z_vals=captured["z_vals"],
+             loss=np.array(float(loss)), r=np.array(r), mask_weight=np.array(mask_weight), warmup=np.array(warmup),
+             no_albedo=np.array(no_albedo), stride=np.array(LARGE_STRIDE))
+    for k in ("color_fine", "weight_sum", "weight_max", "s_val", "gradient_error"):
+        d["out_" + k] = np32(out[k])
+    d["out_gradients_head"] = np32(out["gradients"][:32])        # normals of the first 32 rays
+    d["out_weights_head"] = np32(out["weights"][:32])
+    lsub = lambda t: np.asarray(t, np.float64).reshape(-1)[::LARGE_STRIDE].astype(np.float32)
+    for tag, mod in (("sdf", sdf), ("color", col), ("var", var)):
+        for pname, p in sorted(mod.named_parameters()):
+            if p.grad is None:
+                continue
+            d[f"g_{tag}.{pname}"] = lsub(p.grad.detach().numpy())
+            d[f"n_{tag}.{pname}"] = np.array(float(p.grad.double().norm()))
+    # the float64 oracle on the same inputs, the same jitter-free sample depths
+    sd64 = lambda m: {k: v.detach().double().numpy() for k, v in m.state_dict().items()}
+    c = lambda t: t.detach().numpy()
+    ret, cache = O.render_rnb(sd64(sdf), sd64(col), float(var.variance), c(b["rays_o"]), c(b["rays_d"]), c(b["near"]),
+                              c(b["far"]), c(b["lights_dir"]), None, r, warmup, no_albedo, z_vals=captured["z_vals"].astype(np.float64))
+    o_loss, _, grads, _ = O.train_step_grads(ret, cache, c(b["true_rgb"]), c(mask), 0.1, mask_weight)
+    d["o_loss"] = np.array(float(o_loss))
+    d["o_color_fine"] = np.asarray(ret["color_fine"], np.float32)
+    d["o_weight_sum"] = np.asarray(ret["weight_sum"], np.float32)
+    d["o_gradient_error"] = np.array(float(ret["gradient_error"]))
+    for key, gval in grads.items():
+        d["og_" + key] = lsub(gval)
+        d["on_" + key] = np.array(float(np.linalg.norm(np.asarray(gval, np.float64))))
+    np.savez_compressed(os.path.join(GOLD, f"render512_{name}.npz"), **d)
+    print("large", name, "loss", float(loss), "oracle loss", float(o_loss))
+
+
+def gen_large():
+    gen_render_large("warmup_albedo", True, False)
+    gen_render_large("warmup_noalbedo", True, True)
+    gen_render_large("post_albedo", False, False)
+    gen_render_large("post_noalbedo", False, True)
+    gen_render_large("womask_anneal", False, False, r=0.3, mask_weight=0.0, seed=22)
+
+
 def gen_upsample_search():
     """searchsorted pin: cdf -> inds, samples (models/renderer.py:39-69)."""
     ref = ref_loader.load()
@@ -288,6 +356,9 @@ def gen_background(B=8):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if "--large" in sys.argv:          # only the 512-ray fixtures (about a minute of oracle time each)
+        gen_large()
+        return
     gen_embed()
     gen_sdf(False)
     gen_sdf(True)
@@ -300,6 +371,7 @@ def main():
     gen_render("init_warmup_albedo", True, False, perturb=False, seed=4)
     gen_grid()
     gen_background()
+    gen_large()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
 

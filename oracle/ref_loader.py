@@ -1,4 +1,4 @@
-"""Import the UNMODIFIED reference `models.*` from /root/reference (build container only).
+"""Import the UNMODIFIED reference `models.*` from /root/reference (build container) or its staged copy (GPU box).
 
 TEST INFRASTRUCTURE.  The reference imports `mcubes` and `icecream` at module top
 (models/renderer.py:6-7); both are absent here and neither is used on the hot path,
@@ -13,7 +13,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RNB_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "RNb-NeuS-fork")
+
+
+def _find_root():
+    """RNB_REFERENCE_ROOT, else the build container's /root/reference, else the copy oracle/stage_reference.py put under
+    baseline/_ref (git-ignored; it travels to the GPU box with the snapshot)."""
+    env = os.environ.get("RNB_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(cand, "models", "renderer.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:

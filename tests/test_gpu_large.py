@@ -1,0 +1,180 @@
+"""Parity at the BASELINE.json config size (512 rays = 65 536 fine points, configs 0-2), all four
+{warm-up, post-warm-up} x {albedo, --no_albedo} combinations + womask-anneal, at the north_star tolerances with NO per-tensor
+exceptions: colour / weight_sum / loss <= 1e-3 relative, every parameter tensor cos >= 0.999 and rel-L2 <= 1e-2 -- against
+the REFERENCE's own outputs and gradients (tests/golden/render512_*.npz, written by oracle/gen_golden.py --large from the
+unmodified reference) and against the float64 oracle's gradients stored in the same fixtures.
+Also: the sampling pass (K1) and the fine pass (K2) must agree on the SDF of the same points; the opt-in fused backward
+launch must reproduce the two-kernel backward; the marching-cubes vertex set is pinned to the lattice."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, cosine
+from gpu_common import build_nets, np_state
+from rnb_b200 import synth
+from test_gpu_e2e import make_renderer, loss_fn, cu, FixedRand
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["warmup_albedo", "warmup_noalbedo", "post_albedo", "post_noalbedo", "womask_anneal"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_render_rnb_512_reference_and_oracle(case):
+    g = load_golden("render512_" + case)
+    B, warm, no_albedo, r = int(g["B"]), bool(g["warmup"]), bool(g["no_albedo"]), float(g["r"])
+    renderer, sdf, var, col = make_renderer(True)
+    b = {k: v.cuda() for k, v in synth.make_batch(B, 3, warm, int(g["seed"])).items()}
+    mask = cu(g["mask_used"])
+    args = (b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"])
+    # ---- (a) identical inputs to the fine pass: the reference's own sample depths
+    out = renderer._render_rnb(warm, *args, -1, None, r, no_albedo, _z_vals=cu(g["z_vals"]))
+    c = lambda t: t.detach().cpu().numpy()
+    for k in ("color_fine", "weight_sum", "s_val"):
+        assert rel_l2(c(out[k]), g["out_" + k]) < 1e-3, (k, rel_l2(c(out[k]), g["out_" + k]))
+    assert rel_l2(c(out["gradients"][:32]), g["out_gradients_head"]) < 1e-3          # normals
+    assert abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1) < 1e-3
+    assert rel_l2(c(out["color_fine"]), g["o_color_fine"]) < 1e-3                     # ... and the float64 oracle
+    loss = loss_fn(out, b["true_rgb"], mask, float(g["mask_weight"]))
+    assert abs(float(loss) / float(g["loss"]) - 1) < 1e-3
+    assert abs(float(loss) / float(g["o_loss"]) - 1) < 1e-3
+    loss.backward()
+    st = int(g["stride"])
+    worst, n = {}, 0
+    all_got, all_ref = [], []
+    for tag, mod in (("sdf", sdf), ("color", col), ("var", var)):
+        for pname, p in sorted(mod.named_parameters()):
+            key = f"{tag}.{pname}"
+            if "g_" + key not in g:
+                if tag == "color" and no_albedo:
+                    assert p.grad is None           # reference: no gradient for the colour net with --no_albedo
+                continue
+            if float(g["n_" + key]) < 1e-12:
+                continue
+            got = c(p.grad).reshape(-1)
+            assert np.isfinite(got).all(), key
+            sub = got[::st]
+            okey = "og_variance" if tag == "var" else "og_" + key
+            for name, ref in (("reference", g["g_" + key]), ("oracle", g[okey])):
+                cs, rl = cosine(sub, ref), rel_l2(sub, ref)
+                worst[key + "/" + name] = rl
+                assert cs >= 0.999, (key, name, cs)
+                assert rl <= 1e-2, (key, name, rl)
+            assert abs(np.linalg.norm(got) / float(g["n_" + key]) - 1) < 1e-2, key
+            all_got.append(sub)
+            all_ref.append(g["g_" + key])
+            n += 1
+    assert n >= (26 if no_albedo else 34), n
+    all_got, all_ref = np.concatenate(all_got), np.concatenate(all_ref)
+    assert cosine(all_got, all_ref) > 0.9999 and rel_l2(all_got, all_ref) < 5e-3
+    k_worst = max(worst, key=worst.get)
+    print(f"{case}: worst per-tensor rel-L2 {worst[k_worst]:.2e} ({k_worst}); whole vector {rel_l2(all_got, all_ref):.2e}")
+    # ---- (b) the public call with its own hierarchical sampling (same jitter): the importance samples come from inverting a
+    # CDF built on the coarse SDF, so an SDF that agrees to 3e-4 places them ~1e-4 away -- another quadrature of the same
+    # integrand.  (a) is the control that the fine pass itself holds 1e-3 on identical depths; here the ray integrals and
+    # the loss must still agree to 2e-3 at this ray count (5e-3 was needed on the 16-ray fixtures).
+    fn = renderer.render_rnb_warmup if warm else renderer.render_rnb
+    with FixedRand(torch.from_numpy(g["t_rand"])):
+        out2 = fn(*args, cos_anneal_ratio=r, no_albedo=no_albedo)
+    for k in ("color_fine", "weight_sum"):
+        assert rel_l2(c(out2[k]), g["out_" + k]) < 2e-3, (k, rel_l2(c(out2[k]), g["out_" + k]))
+    loss2 = loss_fn(out2, b["true_rgb"], mask, float(g["mask_weight"]))
+    assert abs(float(loss2) / float(g["loss"]) - 1) < 1e-3
+
+
+def test_sampling_pass_and_fine_pass_agree_on_sdf():
+    """K1 (sdf_fwd: fp32 a_7 in the last dot product) and K2 (sdf_fwd_grad: the fp16 operand image of a_7) evaluate the
+    same network; the sampling pass and the fine pass must not disagree on a point by more than a fraction of the 1e-3
+    parity budget."""
+    from rnb_b200 import kernels as K, ops
+    _, sdf, _, _ = build_nets(True)
+    g = torch.Generator().manual_seed(5)
+    x = ((torch.rand(40000, 3, generator=g) - 0.5) * 2.2).cuda()
+    pk = ops.packed_sdf_nograd(sdf)
+    pts = K.points_explicit(x)
+    s1 = K.sdf_fwd(pk, pts)
+    s2, _, _, _ = K.sdf_fwd_grad(pk, pts, for_backward=False)
+    d = (s1 - s2).abs()
+    scale = s1.abs().max()
+    print("K1 vs K2 sdf: max abs", float(d.max()), "rel-L2", float((s1 - s2).norm() / s1.norm()))
+    assert float((s1 - s2).norm() / s1.norm()) < 1e-4
+    assert float(d.max() / scale) < 2e-4
+
+
+@pytest.mark.parametrize("n_rays", [3, 64])
+def test_fused_backward_launch_matches_two_kernel_path(n_rays, monkeypatch):
+    """RNB_BWD_FUSED=1 (one launch: backward chain + weight-gradient workers fed through per-layer queues) computes the
+    same gradients as the default two-kernel path: same products, another summation order."""
+    from rnb_b200 import kernels as K, ops
+    _, sdf, _, _ = build_nets(True)
+    b = {k: v.cuda() for k, v in synth.make_batch(n_rays, 3, True, 4).items()}
+    pk = ops.packed_sdf_nograd(sdf)
+    z, mid = ops.hierarchical_sample(sdf, b["rays_o"], b["rays_d"], b["near"], b["far"], b["t_rand"], 64, 64, 4)
+    pts = K.points_rays(b["rays_o"], b["rays_d"], mid)
+    st = K.SdfStreams(pts.n_pts, "cuda")
+    K.sdf_fwd_grad(pk, pts, st)
+    n = pts.n_pts
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    d_sdf = torch.randn(n, device="cuda", generator=gen) * 1e-4
+    d_grad = torch.randn(n, 3, device="cuda", generator=gen) * 1e-5
+    d_feat = torch.randn(n, 256, device="cuda", generator=gen) * 1e-7
+    monkeypatch.setenv("RNB_BWD_FUSED", "0")
+    ref = K.sdf_bwd(pk, pts, st, d_sdf, d_grad, d_feat)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("RNB_BWD_FUSED", "1")
+    out = K.sdf_bwd(pk, pts, st, d_sdf, d_grad, d_feat)
+    torch.cuda.synchronize()
+    for l in range(9):
+        for a, r in ((out[0][l], ref[0][l]), (out[1][l], ref[1][l])):
+            assert float((a - r).norm() / r.norm().clamp_min(1e-30)) < 2e-4, l
+
+
+def test_marching_cubes_vertices_pinned_to_lattice_edges():
+    """Table-independent pin of the mesh extractor (reference: mcubes.marching_cubes, models/renderer.py:31; PyMCubes is
+    absent from every environment of this build).  Whatever the triangulation tables, marching cubes places exactly one
+    vertex on every lattice edge whose end points lie on different sides of the threshold, at the linear zero crossing:
+    every emitted vertex must be such a crossing and every sign-changing edge must carry exactly one vertex."""
+    from rnb_b200 import grid
+    _, sdf, _, _ = build_nets(True)
+    R = 40
+    bmin, bmax = torch.tensor([-0.8] * 3), torch.tensor([0.8] * 3)
+    u = grid.sdf_slab(sdf, bmin, bmax, R, 0, R)
+    thr = 0.0
+    verts, tris = grid.marching_cubes_device(u, thr)
+    un = u.double().cpu().numpy()
+    inside = un > thr
+    assert inside.any() and (~inside).any()
+    expected = {}
+    for axis in range(3):
+        a = [slice(None)] * 3
+        bsl = [slice(None)] * 3
+        a[axis], bsl[axis] = slice(0, R - 1), slice(1, R)
+        cross = inside[tuple(a)] != inside[tuple(bsl)]
+        idx = np.argwhere(cross)
+        u0, u1 = un[tuple(a)][cross], un[tuple(bsl)][cross]
+        t = (thr - u0) / (u1 - u0)
+        for (i, j, k), tt in zip(idx, t):
+            p = np.array([i, j, k], np.float64)
+            p[axis] += tt
+            expected[(axis, i, j, k)] = p
+    assert len(verts) == len(expected), (len(verts), len(expected))
+    # match every emitted vertex to its edge: the edge is identified by the two integer coordinates + floor of the third
+    seen = set()
+    for v in verts:
+        frac = np.abs(v - np.round(v))
+        axis = int(np.argmax(frac)) if frac.max() > 1e-9 else None
+        cand = []
+        for ax in ([axis] if axis is not None else [0, 1, 2]):
+            base = np.round(v).astype(int)
+            base[ax] = int(np.floor(v[ax] + 1e-12))
+            for shift in (0, -1):
+                key = (ax, base[0] + (shift if ax == 0 else 0), base[1] + (shift if ax == 1 else 0), base[2] + (shift if ax == 2 else 0))
+                if key in expected and np.abs(expected[key] - v).max() < 2e-4:
+                    cand.append(key)
+        assert cand, v
+        assert cand[0] not in seen, cand[0]
+        seen.add(cand[0])
+    assert len(seen) == len(expected)
+    assert tris.min() == 0 and tris.max() == len(verts) - 1
