@@ -467,11 +467,15 @@ def cuda_reference_section(cx, sizes=(512, 2048), steps=3):
             leaf = lambda m: {k: v.detach().clone().to(cx.dev).requires_grad_(True) for k, v in m.state_dict().items()}
             sdf_sd, col_sd = leaf(sdf), leaf(col)
             variance = var.variance.detach().clone().to(cx.dev).requires_grad_(True)
+        batches = {B: {k: v.to(cx.dev) for k, v in synth.make_batch(B, 3, True, 1).items()} for B in sizes}
+        torch.set_default_tensor_type("torch.cuda.FloatTensor")
         for B in sizes:
-            b = {k: v.to(cx.dev) for k, v in synth.make_batch(B, 3, True, 1).items()}
+            b = batches[B]
 
             def step(i):
-                with torch.device(cx.dev):         # the reference builds its temporaries with bare factory calls
+                # the reference builds its temporaries with bare factory calls and relies on exp_runner.py:669's global
+                # torch.set_default_tensor_type('torch.cuda.FloatTensor') (which the legacy torch.Tensor([...]) honours too)
+                with torch.device(cx.dev):
                     if kind == "reference":
                         for m in (sdf, var, col):
                             m.zero_grad()
@@ -499,6 +503,8 @@ def cuda_reference_section(cx, sizes=(512, 2048), steps=3):
         res["unit"] = "rays/s"
     except Exception as e:  # noqa: BLE001  (a baseline that cannot run must not take the bench line down with it)
         res["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        torch.set_default_tensor_type("torch.FloatTensor")
     torch.cuda.empty_cache()
     return res
 

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ Red
         if (mx > 0.f && isfinite(mx)) {
             int e;
             frexpf(mx, &e);
-            inv_sc = ldexpf(1.f, e - 8);
+            inv_sc = ldexpf(1.f, e - RNB_COT_EXP);
         }
     }
     const float factor = job.use_cot_scale ? job.factor * inv_sc : job.factor;

@@ -56,13 +56,17 @@ __device__ __forceinline__ void load_point(const SdfPointSource& src, int64_t p,
     }
 }
 
+// exponent of the scaled cotangent maximum: the largest input cotangent lands in [2^(RNB_COT_EXP-1), 2^RNB_COT_EXP)
+#ifndef RNB_COT_EXP
+#define RNB_COT_EXP 8
+#endif
 __device__ __forceinline__ float cot_scale_from_max(float m) {
     // power of two that maps the largest input cotangent to [128, 256): keeps every fp16 cotangent operand
     // far from overflow (x256 headroom) while the small ones stay in the normal range
     if (!(m > 0.f) || !isfinite(m)) return 1.f;
     int e;
     frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
-    return ldexpf(1.f, 8 - e);
+    return ldexpf(1.f, RNB_COT_EXP - e);
 }
 
 __device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
