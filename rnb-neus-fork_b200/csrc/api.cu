@@ -9,6 +9,8 @@
 #include <vector>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <mutex>
 
 namespace rnb {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -127,11 +129,14 @@ static const char* const kProfNames[T_COUNT] = {
     "sdf_pack", "sdf_fwd", "sdf_fwd_grad", "sdf_bwd_data", "sdf_bwd_fused", "dw_gemm", "reduce", "absmax", "coarse_z",
     "upsample", "final_merge", "composite_fwd", "composite_bwd", "albedo_pack", "albedo_fwd", "albedo_bwd", "sample_pdf", "nerf_pack", "nerf_fwd", "composite_bg", "ray_batch", "marching_cubes", "adam", "weight_norm"};
 struct ProfRec { int tag; cudaEvent_t a, b; };
-static bool g_prof_on = false;
+// ctypes releases the GIL during a call and the backward runs on the autograd thread: the instrumentation state is shared
+// between threads, so the counters are atomic and the event lists sit behind a mutex
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_ev_pool;
-static long long g_launches[T_COUNT] = {0};
-static cudaEvent_t prof_event() {
+static std::atomic<long long> g_launches[T_COUNT];
+static cudaEvent_t prof_event() {       // caller holds g_prof_mu
     cudaEvent_t e;
     if (!g_ev_pool.empty()) { e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
     cudaEventCreate(&e);
@@ -139,12 +144,17 @@ static cudaEvent_t prof_event() {
 }
 template <class F>
 static cudaError_t profiled(int tag, cudaStream_t st, F&& f) {
-    ++g_launches[tag];
-    if (!g_prof_on) return f();
-    ProfRec r{tag, prof_event(), prof_event()};
+    g_launches[tag].fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return f();
+    ProfRec r;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        r = ProfRec{tag, prof_event(), prof_event()};
+    }
     cudaEventRecord(r.a, st);
     cudaError_t e = f();
     cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(r);
     return e;
 }
@@ -643,14 +653,15 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
 }
 
 
-void rnb_profile_enable(int on) { g_prof_on = on != 0; }
+void rnb_profile_enable(int on) { g_prof_on.store(on != 0); }
 long long rnb_launch_count(void) {
     long long n = 0;
-    for (int t = 0; t < T_COUNT; ++t) n += g_launches[t];
+    for (int t = 0; t < T_COUNT; ++t) n += g_launches[t].load(std::memory_order_relaxed);
     return n;
 }
 int rnb_profile_collect(char* names, int name_stride, float* total_ms, int* counts, int max_tags) {
     cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     float ms[T_COUNT] = {0};
     int cnt[T_COUNT] = {0};
     for (const ProfRec& r : g_prof) {

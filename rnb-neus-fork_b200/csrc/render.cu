@@ -404,9 +404,6 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK, 5) composite_kernel(const
             const float ep = sd[k] - f[k].ic * f[k].dist * 0.5f, en = sd[k] + f[k].ic * f[k].dist * 0.5f;
             dinv += dep * ep + den * en;
             dsdf[k] = (dep + den) * inv_s;
-#ifdef RNB_DEBUG_COMPOSITE
-            if (ray == 13 && lane == 12) printf("k=%d w=%g T=%g alpha=%g raw=%g dw=%g suffix=%g da=%g pc=%g nc=%g dep=%g den=%g dsdf=%g dws=%g total=%g incl=%g\n", k, f[k].w, f[k].T, f[k].alpha, f[k].alpha_raw, dw[k], suffix, da, pc, nc, dep, den, dsdf[k], d_ws, total, incl);
-#endif
             const float dic = (den - dep) * inv_s * f[k].dist * 0.5f;
             const float dtc = dic * (0.5f * (1.f - P.cos_anneal_ratio) * ((-f[k].tc * 0.5f + 0.5f) > 0.f ? 1.f : 0.f) +
                                      P.cos_anneal_ratio * ((-f[k].tc) > 0.f ? 1.f : 0.f));

@@ -21,9 +21,15 @@ def _ops():
     return ops
 
 
-def _wn_linear(n_in, n_out, weight_norm):
-    lin = nn.Linear(n_in, n_out)
-    return lin, weight_norm
+def _warn_forward_only(module, what):
+    """The stand-alone RenderingNetwork.forward / NeRF.forward / render() with n_outside > 0 are forward-only here (their
+    reference callers, validate_mesh_texture and render_novel_image, detach the results).  The reference modules are
+    differentiable: say so loudly instead of silently returning a detached tensor to a caller that trains through them."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        import warnings
+        warnings.warn(f"rnb_b200: {what} is forward-only (no autograd graph is recorded); its result is detached. "
+                      "Train through NeuSRenderer.render_rnb / render_rnb_warmup, or call it under torch.no_grad().",
+                      RuntimeWarning, stacklevel=3)
 
 
 def _use_fused_weight_norm():
@@ -151,6 +157,7 @@ class RenderingNetwork(_WeightNormMLP):
         self.relu = nn.ReLU()
 
     def forward(self, points, normals, view_dirs, feature_vectors):
+        _warn_forward_only(self, "RenderingNetwork.forward called on its own")
         return _ops().albedo_forward(self, points, normals, view_dirs, feature_vectors)
 
 
@@ -184,6 +191,7 @@ class NeRF(nn.Module):
 
     def forward(self, input_pts, input_views):
         assert self.use_viewdirs, "only the use_viewdirs head exists (reference models/fields.py:313-314)"
+        _warn_forward_only(self, "NeRF.forward")
         return _ops().nerf_forward(self, input_pts, input_views)
 
 

@@ -225,11 +225,12 @@ def composite_params(rays_o, rays_d, z, sdf, grad, albedo, lights, variance, cos
     p.variance = L.ptr(variance)
     p.cos_anneal_ratio, p.warmup, p.sample_dist = float(cos_anneal_ratio), int(mode), float(sample_dist)
     p._keep = (lights, rays_o, rays_d, z, sdf, grad, albedo, variance)   # the struct only holds raw pointers
+    p._device = z.device
     return p
 
 
 def composite_fwd(p):
-    B, nl, dev = p.n_rays, p.n_lights, torch.device("cuda", torch.cuda.current_device())
+    B, nl, dev = p.n_rays, p.n_lights, p._device          # outputs live where the inputs live, not on the current device
     f32 = dict(dtype=torch.float32, device=dev)
     out = dict(color=torch.empty(nl, B, 3, **f32), weights=torch.empty(B, 128, **f32), cdf=torch.empty(B, 128, **f32),
                inside=torch.empty(B, 128, **f32), weight_sum=torch.empty(B, 1, **f32),

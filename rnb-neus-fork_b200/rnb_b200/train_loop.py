@@ -49,10 +49,11 @@ def train_rnb(renderer, networks, scene, n_iters, batch_size=512, learning_rate=
     for it in range(n_iters):
         if on_iter:
             on_iter(it)
-        for grp in opt.param_groups:
-            grp["lr"] = learning_rate * (learning_rate_factor(it, warm_up_end, end_iter, learning_rate_alpha)
-                                         if warm_up_end or end_iter != n_iters else 1.0)
+        for grp in opt.param_groups:        # Runner.update_learning_rate runs every iteration (exp_runner.py:320-332)
+            grp["lr"] = learning_rate * learning_rate_factor(it, warm_up_end, end_iter, learning_rate_alpha)
         torch.random.manual_seed(it)                                           # exp_runner.py:170
+        if it > 0 and it % n_images == 0:
+            image_perm = torch.randperm(n_images, generator=g)                 # exp_runner.py:304-306: a new permutation per epoch
         cbn = int(image_perm[it % n_images])
         px = torch.randint(low=0, high=rb.W, size=[batch_size], device="cpu")  # models/dataset.py:356-357
         py = torch.randint(low=0, high=rb.H, size=[batch_size], device="cpu")
