@@ -33,14 +33,15 @@ def _warn_forward_only(module, what):
 
 
 def _use_fused_weight_norm():
-    """The fused fold / VJP replaces 24 small launches per step by 2, which is GPU time saved (graphed 512-ray step 1.57 ->
-    1.51 ms), but its Python autograd node costs more host time than torch's C++ per-layer ops: the eager 512-ray step,
-    which is host-bound, went 2.5 -> 3.5 ms with it.  So it is used where host time does not count -- inside CUDA-graph
-    capture -- unless RNB_FUSED_WN=1 / 0 forces it on / off."""
+    """All layers of a network are folded by ONE launch (rnb_weight_norm_fold) and their VJP is one more
+    (rnb_b200/wnorm.py) instead of torch's 24 per-layer kernels per step -- in eager steps and under CUDA-graph capture
+    alike, so both modes run the same arithmetic.  Round 1 used it only under capture because the node's Python side cost
+    1 ms of host time per 512-ray step; with the layer tables cached it costs what torch's C++ per-layer ops cost
+    (b512_noalbedo 1.97 ms either way, profiles/r02_notes.md).  RNB_FUSED_WN=0 restores torch._weight_norm."""
     force = _os.environ.get("RNB_FUSED_WN")
     if force is not None:
         return force not in ("0", "")
-    return torch.cuda.is_current_stream_capturing()
+    return True
 
 
 class _WeightNormMLP(nn.Module):
@@ -48,9 +49,8 @@ class _WeightNormMLP(nn.Module):
 
     def effective_weights(self):
         """[(W_l fp32 [out,in], b_l)] with weight-norm folded (reference models/fields.py:72-74); autograd turns the
-        kernels' dW into (dg, dv).  While a CUDA graph is being captured all layers are folded by ONE launch
-        (rnb_b200/wnorm.py) and their VJP is one more; otherwise torch's per-layer _weight_norm is used (see
-        _use_fused_weight_norm)."""
+        kernels' dW into (dg, dv).  All layers are folded by ONE launch (rnb_b200/wnorm.py) and their VJP is one more;
+        CPU modules (host-side contract tests) and RNB_FUSED_WN=0 use torch's per-layer _weight_norm."""
         lins = [getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)]
         if all(hasattr(lin, "weight_g") for lin in lins) and lins[0].weight_v.is_cuda and _use_fused_weight_norm():
             from rnb_b200 import wnorm

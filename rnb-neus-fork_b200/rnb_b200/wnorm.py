@@ -24,55 +24,86 @@ def _plan(vs):
     return eo, ro, e, r
 
 
+_PLANS = {}
+
+
+def _cached_plan(vs, gs):
+    """Everything about one set of layers that does not change from step to step: block offsets, and ctypes layer tables
+    with the parameter pointers / shapes already filled in (the parameters are views of FlatAdam's flat buffer or plain
+    nn.Parameters: their addresses are stable).  Building the tables was most of this node's host time, which is what
+    made it slower than torch's per-layer op in eager mode (profiles/r01_notes.md, session 4)."""
+    key = tuple((v.data_ptr(), g.data_ptr(), v.shape[0], v.shape[1]) for v, g in zip(vs, gs))
+    plan = _PLANS.get(key)
+    if plan is None:
+        for t in list(vs) + list(gs):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("rnb_b200.wnorm: weight_v / weight_g must be contiguous float32 tensors")
+        n = len(vs)
+        eo, ro, ne, nr = _plan(vs)
+        fwd, bwd = (L.WnLayer * n)(), (L.WnLayer * n)()
+        for i in range(n):
+            for a in (fwd[i], bwd[i]):
+                a.rows, a.cols = vs[i].shape
+                a.v, a.g = vs[i].data_ptr(), gs[i].data_ptr()
+        plan = dict(n=n, eo=eo, ro=ro, ne=ne, nr=nr, fwd=fwd, bwd=bwd, shapes=[tuple(v.shape) for v in vs],
+                    numel=[v.numel() for v in vs], gshapes=[tuple(g.shape) for g in gs])
+        if len(_PLANS) > 64:
+            _PLANS.clear()
+        _PLANS[key] = plan
+    return plan
+
+
 class _FoldAll(torch.autograd.Function):
     @staticmethod
     def forward(ctx, n, *vg):
         ctx.set_materialize_grads(False)
-        vs = [t.detach() for t in vg[:n]]
-        gs = [t.detach() for t in vg[n:]]
-        for t in vs + gs:
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise RuntimeError("rnb_b200.wnorm: weight_v / weight_g must be contiguous float32 tensors")
-        eo, ro, ne, nr = _plan(vs)
+        vs, gs = vg[:n], vg[n:]
+        plan = _cached_plan(vs, gs)
+        eo, ro = plan["eo"], plan["ro"]
         dev = vs[0].device
-        wbuf = torch.empty(ne, dtype=torch.float32, device=dev)
-        nbuf = torch.empty(nr, dtype=torch.float32, device=dev)
-        arr = (L.WnLayer * n)()
+        wbuf = torch.empty(plan["ne"], dtype=torch.float32, device=dev)
+        nbuf = torch.empty(plan["nr"], dtype=torch.float32, device=dev)
+        arr = plan["fwd"]
         wp, npn = wbuf.data_ptr(), nbuf.data_ptr()
         for i in range(n):
-            a = arr[i]
-            a.rows, a.cols = vs[i].shape
-            a.v, a.g = vs[i].data_ptr(), gs[i].data_ptr()
-            a.w, a.norm = wp + 4 * eo[i], npn + 4 * ro[i]
+            arr[i].w, arr[i].norm = wp + 4 * eo[i], npn + 4 * ro[i]
         L.check(L.load().rnb_weight_norm_fold(arr, n, L.stream_ptr()), "weight_norm_fold")
-        ctx.n, ctx.vs, ctx.gs, ctx.nbuf, ctx.plan = n, vs, gs, nbuf, (eo, ro, ne, nr)
-        return tuple(wbuf[eo[i]:eo[i] + vs[i].numel()].view(vs[i].shape) for i in range(n))
+        ctx.plan, ctx.nbuf, ctx.dev = plan, nbuf, dev
+        return tuple(wbuf[eo[i]:eo[i] + plan["numel"][i]].view(plan["shapes"][i]) for i in range(n))
 
     @staticmethod
     def backward(ctx, *dws):
-        n, vs, gs = ctx.n, ctx.vs, ctx.gs
-        eo, ro, ne, nr = ctx.plan
-        idx = [i for i in range(n) if dws[i] is not None]
+        plan = ctx.plan
+        n, eo, ro = plan["n"], plan["eo"], plan["ro"]
         dvs, dgs = [None] * n, [None] * n
-        if idx:
-            dev = vs[0].device
-            dvbuf = torch.empty(ne, dtype=torch.float32, device=dev)
-            dgbuf = torch.empty(nr, dtype=torch.float32, device=dev)
+        if any(d is not None for d in dws):
+            dvbuf = torch.empty(plan["ne"], dtype=torch.float32, device=ctx.dev)
+            dgbuf = torch.empty(plan["nr"], dtype=torch.float32, device=ctx.dev)
             keep = []
-            arr = (L.WnLayer * len(idx))()
+            arr = plan["bwd"]
             npn, dvp, dgp = ctx.nbuf.data_ptr(), dvbuf.data_ptr(), dgbuf.data_ptr()
-            for k, i in enumerate(idx):
+            k = 0
+            for i in range(n):
                 dw = dws[i]
+                if dw is None:
+                    continue
                 if dw.dtype != torch.float32 or not dw.is_contiguous():
                     dw = dw.float().contiguous()
                 keep.append(dw)
                 a = arr[k]
-                a.rows, a.cols = vs[i].shape
-                a.v, a.g, a.w = vs[i].data_ptr(), gs[i].data_ptr(), dw.data_ptr()
+                if k != i:       # compact the table when some layers received no gradient (rows/cols/v/g of layer i)
+                    src = plan["fwd"][i]
+                    a.rows, a.cols, a.v, a.g = src.rows, src.cols, src.v, src.g
+                a.w = dw.data_ptr()
                 a.norm, a.dv, a.dg = npn + 4 * ro[i], dvp + 4 * eo[i], dgp + 4 * ro[i]
-                dvs[i] = dvbuf[eo[i]:eo[i] + vs[i].numel()].view(vs[i].shape)
-                dgs[i] = dgbuf[ro[i]:ro[i] + vs[i].shape[0]].view(gs[i].shape)
-            L.check(L.load().rnb_weight_norm_vjp(arr, len(idx), L.stream_ptr()), "weight_norm_vjp")
+                dvs[i] = dvbuf[eo[i]:eo[i] + plan["numel"][i]].view(plan["shapes"][i])
+                dgs[i] = dgbuf[ro[i]:ro[i] + plan["shapes"][i][0]].view(plan["gshapes"][i])
+                k += 1
+            L.check(L.load().rnb_weight_norm_vjp(arr, k, L.stream_ptr()), "weight_norm_vjp")
+            if k != n:           # the compacted table no longer matches the layer order: rebuild it next time
+                for i in range(n):
+                    src, a = plan["fwd"][i], arr[i]
+                    a.rows, a.cols, a.v, a.g = src.rows, src.cols, src.v, src.g
         return (None, *dvs, *dgs)
 
 
