@@ -14,6 +14,23 @@ constexpr int RAYS_PER_BLOCK = 4;          // 4 warps, one ray each
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU-only forms for the adjoint kernel (no IEEE division / sqrt subroutine calls): ex2.approx, rcp.approx, rsqrt.approx
+// are accurate to ~2 ulp, four orders of magnitude inside the 2e-3 the adjoint is checked at
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    return rcp_fast(1.f + e);
+}
 
 // torch.linspace(start, end, steps) float32 arithmetic (ATen: start + step*i below the midpoint, end - step*(steps-1-i) above)
 __device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
@@ -240,27 +257,47 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) final_merge_kernel(const 
 // ------------------------------------------------------------------------------------------------ A12-A13
 struct SampleFw {
     float dist, alpha, alpha_raw, pc, nc, T, w, tc, ic, gn, relax, inside;
+    float rq, rgn;      // FAST only: 1 / (pc + 1e-5), 1 / |g|
 };
 
 // per-sample forward quantities of render_core_mvps (renderer.py:503-540); T and w are filled by the caller
+// FAST (the adjoint kernel): the same quantities from MUFU approximations; the forward kernels keep the IEEE forms their
+// outputs (weights, cdf, inside_sphere) are pinned with.
+template <bool FAST = false>
 __device__ __forceinline__ void sample_forward(float sdf, const float (&g)[3], const float (&d)[3], const float (&pt)[3],
                                                float dist, float inv_s, float r, SampleFw& f) {
     f.dist = dist;
     f.tc = d[0] * g[0] + d[1] * g[1] + d[2] * g[2];
     f.ic = -(fmaxf(-f.tc * 0.5f + 0.5f, 0.f) * (1.f - r) + fmaxf(-f.tc, 0.f) * r);
     const float en = sdf + f.ic * dist * 0.5f, ep = sdf - f.ic * dist * 0.5f;
-    f.pc = sigmoidf_acc(ep * inv_s);
-    f.nc = sigmoidf_acc(en * inv_s);
-    f.alpha_raw = (f.pc - f.nc + 1e-5f) / (f.pc + 1e-5f);
+    const float p2 = pt[0] * pt[0] + pt[1] * pt[1] + pt[2] * pt[2];
+    const float g2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+    if (FAST) {
+        f.pc = sigmoidf_fast(ep * inv_s);
+        f.nc = sigmoidf_fast(en * inv_s);
+        f.rq = rcp_fast(f.pc + 1e-5f);
+        f.alpha_raw = (f.pc - f.nc + 1e-5f) * f.rq;
+        f.relax = p2 < 1.44f ? 1.f : 0.f;
+        f.inside = 0.f;
+        f.rgn = g2 > 0.f ? rsqrt_fast(g2) : 0.f;
+        f.gn = g2 * f.rgn;
+    } else {
+        f.pc = sigmoidf_acc(ep * inv_s);
+        f.nc = sigmoidf_acc(en * inv_s);
+        f.alpha_raw = (f.pc - f.nc + 1e-5f) / (f.pc + 1e-5f);
+        const float pn = sqrtf(p2);
+        f.inside = pn < 1.f ? 1.f : 0.f;
+        f.relax = pn < 1.2f ? 1.f : 0.f;
+        f.gn = sqrtf(g2);
+    }
     f.alpha = fminf(fmaxf(f.alpha_raw, 0.f), 1.f);
-    const float pn = sqrtf(pt[0] * pt[0] + pt[1] * pt[1] + pt[2] * pt[2]);
-    f.inside = pn < 1.f ? 1.f : 0.f;
-    f.relax = pn < 1.2f ? 1.f : 0.f;
-    f.gn = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
 }
 
+#ifndef RNB_COMP_BLOCKS
+#define RNB_COMP_BLOCKS 5
+#endif
 template <bool BWD>
-__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK, 5) composite_kernel(const __grid_constant__ CompositeParams P) {
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK, RNB_COMP_BLOCKS) composite_kernel(const __grid_constant__ CompositeParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ray = blockIdx.x * RAYS_PER_BLOCK + warp;
     if (ray >= P.n_rays) return;
@@ -304,7 +341,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK, 5) composite_kernel(const
         const float dist = (lane == 31 && k == 3) ? P.sample_dist : zn - zz[k];
         const float mid = zz[k] + dist * 0.5f;
         const float pt[3] = {o[0] + d[0] * mid, o[1] + d[1] * mid, o[2] + d[2] * mid};
-        sample_forward(sd[k], g[k], d, pt, dist, inv_s, P.cos_anneal_ratio, f[k]);
+        sample_forward<BWD>(sd[k], g[k], d, pt, dist, inv_s, P.cos_anneal_ratio, f[k]);
         run *= 1.f - f[k].alpha + 1e-7f;
     }
     {
@@ -394,12 +431,13 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK, 5) composite_kernel(const
         float dsdf[4], dinv = 0.f;
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
-            float da = f[k].T * dw[k] - suffix / (1.f - f[k].alpha + 1e-7f);
+            float da = f[k].T * dw[k] - suffix * rcp_fast(1.f - f[k].alpha + 1e-7f);
             suffix += ww[k];
             if (!(f[k].alpha_raw >= 0.f && f[k].alpha_raw <= 1.f)) da = 0.f;
-            const float pc = f[k].pc, nc = f[k].nc, q = pc + 1e-5f;
-            const float dpc = da * (1.f / q - (pc - nc + 1e-5f) / (q * q));
-            const float dnc = -da / q;
+            // alpha = (pc - nc + 1e-5) / q, q = pc + 1e-5:  d alpha / d pc = (1 - alpha) / q,  d alpha / d nc = -1 / q
+            const float pc = f[k].pc, nc = f[k].nc;
+            const float dnc = -da * f[k].rq;
+            const float dpc = -dnc * (1.f - f[k].alpha_raw);
             const float dep = dpc * pc * (1.f - pc), den = dnc * nc * (1.f - nc);
             const float ep = sd[k] - f[k].ic * f[k].dist * 0.5f, en = sd[k] + f[k].ic * f[k].dist * 0.5f;
             dinv += dep * ep + den * en;
@@ -407,7 +445,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK, 5) composite_kernel(const
             const float dic = (den - dep) * inv_s * f[k].dist * 0.5f;
             const float dtc = dic * (0.5f * (1.f - P.cos_anneal_ratio) * ((-f[k].tc * 0.5f + 0.5f) > 0.f ? 1.f : 0.f) +
                                      P.cos_anneal_ratio * ((-f[k].tc) > 0.f ? 1.f : 0.f));
-            const float ek = f[k].gn > 0.f ? eik_coef * f[k].relax * (f[k].gn - 1.f) / f[k].gn : 0.f;
+            const float ek = eik_coef * f[k].relax * (1.f - f[k].rgn) * (f[k].rgn > 0.f ? 1.f : 0.f);      // (|g| - 1) / |g|
 #pragma unroll
             for (int j = 0; j < 3; ++j) dg[k][j] += dtc * d[j] + ek * g[k][j];
         }
