@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
         for (int t = 0; t < n_my; ++t) {
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
             const bool live = p < P.src.n_pts;
-            // dz2 = d_albedo * albedo (1 - albedo)   (sigmoid'), kept unscaled for dW_2 / db_2
+            // dz2 = d_albedo * albedo (1 - albedo)   (sigmoid'); its scaled fp16 image is a 16-wide stream, the B operand of
+            // the dW_2 = dz2^T h_1 job of the weight-gradient GEMM
             float dz2[3] = {0.f, 0.f, 0.f};
             if (live) {
 #pragma unroll
@@ -172,8 +173,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) albedo_bwd_kernel(const __gr
                 }
             }
             if (ep.half == 0) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) P.dz2[(size_t)k * P.n_pad + p] = dz2[k];
+                const uint4 u0 = make_uint4(pack_h2_sat(dz2[0] * scale, dz2[1] * scale), pack_h2_sat(dz2[2] * scale, 0.f), 0u, 0u);
+                st_stream(P.st_dz2, p, 0, 2, u0);
+                st_stream(P.st_dz2, p, 1, 2, make_uint4(0u, 0u, 0u, 0u));
             }
             // dz1 = (W2^T dz2) * (h1 > 0)
 #pragma unroll 4

@@ -44,7 +44,7 @@ struct AlbedoBwdParams {
     const uint8_t* st_h0;
     const uint8_t* st_h1;
     int64_t n_pad;
-    float* dz2;                // out [3][n_pad] fp32 (unscaled)
+    uint8_t* st_dz2;           // out fp16 stream [Npad x 16] (scaled): columns 0..2 = dz2, the rest zero
     uint8_t* st_dz1;           // out fp16 stream (scaled)
     uint8_t* st_dz0;           // out fp16 stream (scaled)
     float* d_feat;             // out [n,256] fp32 (optional)

@@ -63,11 +63,11 @@ static AlbedoBwdScratch albedo_bwd_scratch(int64_t n_pts) {
     size_t o = 0;
     L.absmax = o; o += 256;
     L.sum_part = o; o += 3 * 256;
-    L.dz2 = o; o += align_up((size_t)3 * n_pad * 4, 256);
+    L.dz2 = o; o += align_up((size_t)n_pad * 32, 256);          // fp16 stream [n_pad x 16]
     L.dz1 = o; o += s256;
     L.dz0 = o; o += s256;
     o = align_up(o, 256);
-    L.dw_part = o; o += (size_t)L.dw_splits * 256 * (256 + 256 + 64) * 4;
+    L.dw_part = o; o += (size_t)L.dw_splits * 256 * (256 + 256 + 64 + 16) * 4;
     L.dwcs_part = o; o += (size_t)2 * L.dw_splits * 256 * 2 * 4;      // two column-sum partials per split (dw_gemm_kernel)
     L.cs_part = o; o += (size_t)2 * L.dw_splits * (3 * 256 + 4) * 4;  // W_2: three weighted sums + the weight sums
     L.total = align_up(o, 256);
@@ -591,7 +591,7 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     P.normals = normals; P.albedo = albedo; P.d_albedo = d_albedo; P.cot_absmax = absmax;
     P.st_h0 = (const uint8_t*)st_h0; P.st_h1 = (const uint8_t*)st_h1;
     P.n_pad = n_pad;
-    P.dz2 = (float*)(sc + L.dz2);
+    P.st_dz2 = sc + L.dz2;
     P.st_dz1 = sc + L.dz1; P.st_dz0 = sc + L.dz0;
     P.d_feat = d_feat; P.d_normal = d_normal;
     P.st_dfeat16 = (uint8_t*)d_feat16; P.dfeat_max = absmax + 1;
@@ -605,7 +605,7 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
     float* part = (float*)(sc + L.dw_part);
     float* dwcs = (float*)(sc + L.dwcs_part);
     auto add_dw = [&](const uint8_t* a, const uint8_t* b, int b_chunks, int nw, float* dst, int pitch, int col0, int out_cols,
-                      float* db_dst) -> DwJob& {
+                      float* db_dst) {
         DwJob& j = D.jobs[D.n_jobs++];
         j.n_pairs = j.mma_pairs = 1; j.a[0] = a; j.b[0] = b; j.b_chunk0 = 0; j.nw = nw; j.partial = part;
         for (int k = 0; k < DW_MAX_PAIRS; ++k) j.b_chunks[k] = b_chunks;
@@ -622,30 +622,28 @@ int rnb_albedo_bwd(const rnb_points_t* pts, const float* normals, const float* a
         r.dst = dst; r.dst_pitch = pitch; r.dst_row0 = 0; r.dst_col0 = col0; r.out_rows = 256; r.out_cols = out_cols;
         r.factor = 1.f; r.use_cot_scale = 1;
         part += (size_t)L.dw_splits * 256 * nw;
-        return j;
     };
-    DwJob& j1 = add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256, db1);
+    add_dw(sc + L.dz1, (const uint8_t*)st_h0, 32, 256, dW1, 256, 0, 256, db1);
     add_dw(sc + L.dz0, (const uint8_t*)st_feat, 32, 256, dW0, 310, 54, 256, db0);
     add_dw(sc + L.dz0, (const uint8_t*)st_pe, 8, 64, dW0, 310, 0, 54, nullptr);
     {
         // dW_2[k,:] = sum_p dz2[k,p] h_1[p,:] and db_2[k] = sum_p dz2[k,p], k = 0..2 (the 3-wide output layer,
-        // models/fields.py:203-214): the first job also stages the h_1 tiles and takes three weighted column sums
-        j1.n_pairs = 2;
-        j1.a[1] = (const uint8_t*)st_h1;
-        DwColsum& c = j1.cs[j1.n_cs++];
-        c.pair = 1; c.tile_off = 0; c.width = 256; c.n_w = 3; c.n_valid = n_pad;
+        // models/fields.py:203-214): one more job of the same GEMM, D[256 x 16] = h_1^T dz2 with the 16-wide dz2 stream as
+        // its B operand, written transposed into dW_2 [3,256]; db_2 = the column sums of the staged dz2 tile
+        DwJob& j = D.jobs[D.n_jobs++];
+        j.n_pairs = j.mma_pairs = 1; j.a[0] = (const uint8_t*)st_h1; j.b[0] = sc + L.dz2; j.b_chunk0 = 0; j.nw = 16; j.partial = part;
+        for (int k = 0; k < DW_MAX_PAIRS; ++k) j.b_chunks[k] = 2;
         float* cpart = (float*)(sc + L.cs_part);
-        c.wsum_partial = cpart + (size_t)3 * 2 * L.dw_splits * 256;
-        for (int k = 0; k < 3; ++k) {
-            c.w[k] = P.dz2 + (size_t)k * n_pad;
-            c.partial[k] = cpart + (size_t)k * 2 * L.dw_splits * 256;
-            ReduceJob& r = R.jobs[R.n_jobs++];
-            r.partial = c.partial[k]; r.splits = 2 * L.dw_splits; r.rows = 1; r.nw = 256;
-            r.dst = dW2 + k * 256; r.dst_pitch = 0; r.out_rows = 1; r.out_cols = 256; r.factor = 1.f; r.use_cot_scale = 0;
-            ReduceJob& rs = R.jobs[R.n_jobs++];
-            rs.partial = c.wsum_partial + k; rs.splits = 2 * L.dw_splits; rs.rows = 1; rs.nw = 4;
-            rs.dst = db2 + k; rs.dst_pitch = 0; rs.out_rows = 1; rs.out_cols = 1; rs.factor = 1.f; rs.use_cot_scale = 0;
-        }
+        DwColsum& c = j.cs[j.n_cs++];
+        c.pair = 0; c.tile_off = 32768; c.width = 16; c.n_w = 0; c.partial[0] = cpart;
+        ReduceJob& rb = R.jobs[R.n_jobs++];
+        rb.partial = cpart; rb.splits = 2 * L.dw_splits; rb.rows = 1; rb.nw = 256;
+        rb.dst = db2; rb.dst_pitch = 0; rb.out_rows = 1; rb.out_cols = 3; rb.factor = 1.f; rb.use_cot_scale = 1;
+        ReduceJob& r = R.jobs[R.n_jobs++];
+        r.partial = part; r.splits = L.dw_splits; r.rows = 256; r.nw = 16;
+        r.dst = dW2; r.dst_pitch = 1; r.dst_row0 = 0; r.dst_col0 = 0; r.dst_col_stride = 256; r.out_rows = 256; r.out_cols = 3;
+        r.factor = 1.f; r.use_cot_scale = 1;
+        part += (size_t)L.dw_splits * 256 * 16;
     }
     e = profiled(T_DW_GEMM, st, [&] { return launch_dw_gemm(D, L.dw_splits, st); });
     if (e != cudaSuccess) return (int)e;

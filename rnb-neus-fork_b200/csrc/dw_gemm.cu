@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const __grid_con
                     float4* dst = reinterpret_cast<float4*>(out + (size_t)(h * 128 + row) * nw + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        if (c0 + 4 * j < nw)          // nw = 16: only the first 16 of the 32 loaded columns exist
+                            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 }
         } else {
             for (int c = 0; c < nw; ++c) out[(size_t)(grp * 128 + row) * nw + c] = 0.f;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const __grid_constant__ Red
         for (int s = 0; s < job.splits2; ++s) acc2 += s2[(size_t)s * stride];
         acc += acc2 * (job.use_cot_scale2 ? job.factor2 * inv_sc : job.factor2);
     }
-    float* dst = job.dst + (size_t)(job.dst_row0 + m) * job.dst_pitch + job.dst_col0 + n;
+    float* dst = job.dst + (size_t)(job.dst_row0 + m) * job.dst_pitch + (size_t)(job.dst_col0 + n) * (job.dst_col_stride ? job.dst_col_stride : 1);
     *dst = job.accumulate ? *dst + acc : acc;
 }
 

@@ -53,6 +53,7 @@ struct ReduceJob {
     int splits, rows, nw;
     float* dst;               // row-major, pitch dst_pitch floats
     int dst_pitch, dst_row0, dst_col0;
+    int dst_col_stride;       // distance between output columns (0 = 1): dst_pitch = 1 with a column stride writes transposed
     int out_rows, out_cols;
     const float* partial2;    // optional second source with its own scaling (same shape), null = none
     int splits2;

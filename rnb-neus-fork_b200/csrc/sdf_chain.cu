@@ -796,8 +796,9 @@ __device__ __forceinline__ void fused_dw_worker(uint8_t* smem, const SdfBwdFused
                     float4* dst = reinterpret_cast<float4*>(out + (size_t)(h * 128 + row) * nw + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        if (c0 + 4 * j < nw)          // nw = 16: only the first 16 of the 32 loaded columns exist
+                            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 }
         } else {
             for (int h = 0; h < 2; ++h)
