@@ -117,9 +117,45 @@ def launches(path, top=30):
         print(f"| `{k}` | {n} | {us:.1f} | {100 * us / total:.1f}% |")
 
 
+def traffic(reps, points, out_path):
+    """profiles/r02_traffic.json: dram__bytes_read + dram__bytes_write per point of every kernel in the reports, stamped with
+    the hash of the kernel sources (bench.source_sha) -- bench.py prints roofline.traffic only while that hash matches."""
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import source_sha
+    kernels = {}
+    for rep in reps:
+        rows = ncu_csv(rep, "raw")
+        hdr = rows[0]
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            name = d["Kernel Name"].split("(")[0].replace("rnb::", "").replace("_kernel", "")
+            try:
+                rd, wr = float(d["dram__bytes_read.sum"]), float(d["dram__bytes_write.sum"])
+            except (KeyError, ValueError):
+                continue
+            units = dict(zip(hdr, rows[1]))
+
+            def to_bytes(v, u):
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            tot = to_bytes(rd, units["dram__bytes_read.sum"]) + to_bytes(wr, units["dram__bytes_write.sum"])
+            k = kernels.setdefault(name, dict(launches=0, dram_bytes=0.0))
+            k["launches"] += 1
+            k["dram_bytes"] += tot
+    out = dict(source_sha=source_sha(), points=points, capture=", ".join(os.path.basename(r) for r in reps), kernels={})
+    for name, k in kernels.items():
+        out["kernels"][name] = dict(dram_bytes_per_launch=k["dram_bytes"] / k["launches"],
+                                    dram_bytes_per_point=k["dram_bytes"] / k["launches"] / points, launches_captured=k["launches"])
+    json.dump(out, open(out_path, "w"), indent=1)
+    print("wrote", out_path, {k: round(v["dram_bytes_per_point"]) for k, v in out["kernels"].items()})
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
-    if args and args[0] == "--launches":
+    if args and args[0] == "--traffic":      # --traffic POINTS out.json rep [rep ...]
+        traffic(args[3:], int(args[1]), args[2])
+    elif args and args[0] == "--launches":
         for p in args[1:]:
             launches(p)
     else:
