@@ -43,6 +43,62 @@ __global__ void __launch_bounds__(128) bulk_unicast(const __grid_constant__ Prob
     __syncthreads();
 }
 
+// every slice is fetched by SPLIT lanes, each copying 1/SPLIT of it (same barrier): does a slice land sooner when its bytes
+// come as several concurrent copies?
+template <int SPLIT>
+__global__ void __launch_bounds__(128) bulk_split(const __grid_constant__ ProbeParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t full[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.stages; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const unsigned long long mask = P.ws_bytes - 1;
+        unsigned long long off = ((unsigned long long)blockIdx.x * P.stride_ctas * P.slice) & mask;
+        const uint32_t part = P.slice / SPLIT;
+        for (int it = 0; it < P.iters + P.stages; ++it) {
+            const int slot = it % P.stages;
+            if (it >= P.stages) mbar_wait(&full[slot], ((it / P.stages) - 1) & 1);
+            if (it < P.iters) {
+                if (lane == 0) mbar_expect_tx(&full[slot], P.slice);
+                __syncwarp();
+                if (lane < SPLIT) bulk_g2s(smem + (size_t)slot * P.slice + lane * part, P.src + off + lane * part, part, &full[slot]);
+                off = (off + P.slice) & mask;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// one issuing lane PER SLOT: lane s refills slot s as soon as it has seen it full (do the per-copy issue costs overlap?)
+__global__ void __launch_bounds__(128) bulk_lanes(const __grid_constant__ ProbeParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t full[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.stages; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < P.stages) {
+        const int slot = threadIdx.x;
+        const unsigned long long mask = P.ws_bytes - 1;
+        unsigned long long off = ((unsigned long long)blockIdx.x * P.stride_ctas * P.slice + (unsigned long long)slot * P.slice) & mask;
+        const int n = P.iters / P.stages;
+        for (int it = 0; it <= n; ++it) {
+            if (it > 0) mbar_wait(&full[slot], (it - 1) & 1);
+            if (it < n) {
+                mbar_expect_tx(&full[slot], P.slice);
+                bulk_g2s(smem + (size_t)slot * P.slice, P.src + off, P.slice, &full[slot]);
+                off = (off + (unsigned long long)P.stages * P.slice) & mask;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
@@ -128,8 +184,8 @@ int main() {
                tbs, bytes / (ms * 1e-3) / (clk_khz * 1e3) / sm);
         fflush(stdout);
     };
-    const unsigned long long ws_list[] = {2ull << 20, 32ull << 20, 256ull << 20};
-    const int slice_list[] = {8192, 16384, 32768};
+    const unsigned long long ws_list[] = {2ull << 20};
+    const int slice_list[] = {16384, 32768};
     const int stage_list[] = {3, 6};
     for (unsigned long long ws : ws_list)
         for (int slice : slice_list)
@@ -150,6 +206,33 @@ int main() {
                     float ms = 0;
                     cudaEventElapsedTime(&ms, e0, e1);
                     report("unicast", P, cps, (double)grid * P.iters * slice, ms);
+                    cudaFuncSetAttribute((const void*)bulk_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    for (int rep = 0; rep < 2; ++rep) {
+                        cudaEventRecord(e0);
+                        bulk_lanes<<<grid, 128, smem>>>(P);
+                        cudaEventRecord(e1);
+                        cudaEventSynchronize(e1);
+                    }
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    report("lanes", P, cps, (double)grid * (P.iters / stages) * stages * slice, ms);
+                    cudaFuncSetAttribute((const void*)bulk_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    cudaFuncSetAttribute((const void*)bulk_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    for (int rep = 0; rep < 2; ++rep) {
+                        cudaEventRecord(e0);
+                        bulk_split<2><<<grid, 128, smem>>>(P);
+                        cudaEventRecord(e1);
+                        cudaEventSynchronize(e1);
+                    }
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    report("split2", P, cps, (double)grid * P.iters * slice, ms);
+                    for (int rep = 0; rep < 2; ++rep) {
+                        cudaEventRecord(e0);
+                        bulk_split<4><<<grid, 128, smem>>>(P);
+                        cudaEventRecord(e1);
+                        cudaEventSynchronize(e1);
+                    }
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    report("split4", P, cps, (double)grid * P.iters * slice, ms);
                     for (int rep = 0; rep < 2; ++rep) {
                         cudaEventRecord(e0);
                         bulk_multicast<<<grid, 128, smem>>>(P);
