@@ -509,7 +509,7 @@ def cuda_reference_section(cx, sizes=(512, 2048), steps=3):
     return res
 
 
-def dp_check(cx, train_step, red, batches):
+def dp_check(cx, train_step, red, batches, exact=None):
     """Data-parallel equivalence with the real kernels under NCCL (reference seam exp_runner.py:170, 194):
     one untimed step -- every rank keeps its pre-reduction flat gradient, all ranks gather them, and the all-reduced
     buffer must equal their mean in the rank order NCCL is NOT obliged to use, so the comparison is to fp32 rounding of a
@@ -529,8 +529,51 @@ def dp_check(cx, train_step, red, batches):
     distinct = all(not torch.equal(rays[0], r) for r in rays[1:])
     differ = float((gathered[0] - gathered[-1]).norm() / gathered[0].norm().clamp_min(1e-30))
     ok = err < 1e-6 and distinct and differ > 1e-3
-    return dict(status="ok" if ok else "FAILED", allreduce_vs_mean_of_ranks_rel_l2=err, ranks_drew_distinct_rays=distinct,
-                rank_gradients_differ_rel_l2=differ, flat_buffer_bytes=red.nbytes)
+    res = dict(status="ok" if ok else "FAILED", allreduce_vs_mean_of_ranks_rel_l2=err, ranks_drew_distinct_rays=distinct,
+               rank_gradients_differ_rel_l2=differ, flat_buffer_bytes=red.nbytes)
+    if exact is not None:
+        res["exact_global_batch"] = exact()
+        if res["exact_global_batch"]["rel_l2_vs_single_process_batch"] > 5e-3:
+            res["status"] = "FAILED"
+    return res
+
+
+def exact_batch_check(cx, renderer, red, no_albedo, rays=256):
+    """parallel.ExactBatch under NCCL with the real kernels: `world` ranks x `rays` rays (eikonal numerator / count and
+    mask_sum summed over the ranks, gradient shares summed) against ONE process rendering the concatenated batch with the
+    reference's loss.  Jitter off (perturb_overwrite = 0) so both see the same sample depths."""
+    from rnb_b200 import synth
+    from rnb_b200.parallel import ExactBatch
+    dist = cx.dist
+    b = {k: v.to(cx.dev) for k, v in synth.make_batch(rays, 3, True, 100 + cx.rank).items()}
+    keys = ("rays_o", "rays_d", "near", "far", "true_rgb", "mask")
+    big = {}
+    for k in keys:
+        parts = [torch.empty_like(b[k]) for _ in range(cx.world)]
+        dist.all_gather(parts, b[k].contiguous())
+        big[k] = torch.cat(parts, 1 if k == "true_rgb" else 0)
+    lights = b["lights_dir"].clone()
+    dist.broadcast(lights, 0)                      # warm-up mode: one light set per view, shared by all rays
+    # (1) one process, the whole batch, the reference's loss
+    red.zero()
+    out = renderer.render_rnb_warmup(big["rays_o"], big["rays_d"], big["near"], big["far"], lights, perturb_overwrite=0,
+                                     cos_anneal_ratio=1.0, no_albedo=no_albedo)
+    loss_big = loss_fn(out, big["true_rgb"], big["mask"])
+    loss_big.backward()
+    g_big = red.collect().clone()
+    # (2) ExactBatch: every rank its own rays
+    eb = ExactBatch(renderer)
+    red.zero()
+    out = renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], lights, perturb_overwrite=0,
+                                     cos_anneal_ratio=1.0, no_albedo=no_albedo)
+    share = eb.loss(out, b["true_rgb"], b["mask"])
+    share.backward()
+    g_dp = red.all_reduce_sum().clone()
+    total = eb.total(share, out)
+    renderer.dp_exact_group = None
+    rel = float((g_dp - g_big).norm() / g_big.norm().clamp_min(1e-30))
+    return dict(rays_per_rank=rays, rel_l2_vs_single_process_batch=rel, loss_single_process=float(loss_big),
+                loss_from_shares=float(total))
 
 
 def main():
@@ -638,7 +681,8 @@ def main():
     clk = ClockSampler(cx.local)
     for i in range(args.warmup):
         step(i)
-    check = dp_check(cx, fwd_bwd, red, dev_b) if (world > 1 and not render_bg) else None
+    check = dp_check(cx, fwd_bwd, red, dev_b, exact=(lambda: exact_batch_check(cx, renderer, red, no_albedo))
+                     if not args.graph else None) if (world > 1 and not render_bg) else None
     L.profile_enable(True)
     n0 = L.launch_count()
     cx.sync_all()

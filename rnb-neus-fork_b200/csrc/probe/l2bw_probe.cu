@@ -185,8 +185,8 @@ int main() {
         fflush(stdout);
     };
     const unsigned long long ws_list[] = {2ull << 20};
-    const int slice_list[] = {16384, 32768};
-    const int stage_list[] = {3, 6};
+    const int slice_list[] = {4096, 8192, 16384};
+    const int stage_list[] = {3, 6, 12};
     for (unsigned long long ws : ws_list)
         for (int slice : slice_list)
             for (int stages : stage_list)

@@ -74,6 +74,10 @@ class NeuSRenderer:
         self.up_sample_steps = up_sample_steps
         self.perturb = perturb
         self.color_depth = 3          # the Runner overwrites it after construction (reference exp_runner.py:125)
+        # data-parallel option (rnb_b200.parallel.ExactBatch): None = every rank normalises by its own batch (DDP
+        # semantics); a process group (or True for the default group) = the eikonal mean of render_rnb* runs over the
+        # points of all ranks, so that N ranks x B rays reproduce one N*B-ray batch exactly
+        self.dp_exact_group = None
 
     # ------------------------------------------------------------------ sampling
     def _jitter(self, batch_size, device, perturb_overwrite):
@@ -152,7 +156,7 @@ class NeuSRenderer:
         (color_fine, weight_sum, gradient_error, weights, cdf, inside, weight_max, gradients, sdf,
          _albedo) = _ops.rnb_fine(self.sdf_network, self.color_network, self.deviation_network.variance, rays_o, rays_d,
                                   z_vals, mid_z, lights_dir, cos_anneal_ratio, 1 if warmup else 0, not no_albedo,
-                                  2.0 / self.n_samples, folded=folded)
+                                  2.0 / self.n_samples, folded=folded, dp_group=self.dp_exact_group)
         inv_s = torch.exp(self.deviation_network.variance.detach() * 10.0).clip(1e-6, 1e6)
         s_val = (1.0 / inv_s).expand(batch_size, 1)
         return {

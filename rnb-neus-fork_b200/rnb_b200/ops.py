@@ -245,6 +245,12 @@ class _RnbFine(torch.autograd.Function):
                                 meta["mode"], meta["sample_dist"])
         out = K.composite_fwd(cp)
         eik = out["eik_part"].sum(0)
+        if meta.get("dp_group") is not None:
+            # exact global-batch normaliser (parallel.ExactBatch): the eikonal mean runs over the points of ALL ranks --
+            # numerator and count (reference models/renderer.py:540) are summed over the group, two floats in one all-reduce.
+            # The backward differentiates the global ratio through this rank's points only: exactly its share.
+            import torch.distributed as dist
+            dist.all_reduce(eik, op=dist.ReduceOp.SUM, group=meta["dp_group"] if meta["dp_group"] is not True else None)
         grad_err = eik[0] / (eik[1] + 1e-5)
         ctx.pk, ctx.pts, ctx.streams, ctx.cp = pk, pts, streams, cp
         ctx.eik_den = eik[1:2].contiguous()
@@ -313,7 +319,7 @@ def _rnb_fine_inference(sdf_module, color_module, variance, o, d, z_vals, mid_z,
 
 
 def rnb_fine(sdf_module, color_module, variance, rays_o, rays_d, z_vals, mid_z, lights, cos_anneal_ratio, mode,
-             use_albedo, sample_dist, folded=None):
+             use_albedo, sample_dist, folded=None, dp_group=None):
     """mode 0: render_rnb, 1: render_rnb_warmup, 2: plain colour (render).  folded: (flat, pk) of fold_and_pack."""
     if z_vals.shape[1] != FINE_SAMPLES:
         raise RuntimeError(f"rnb_b200: the fine pass is specialised for n_samples + n_importance = {FINE_SAMPLES} "
@@ -324,7 +330,7 @@ def rnb_fine(sdf_module, color_module, variance, rays_o, rays_d, z_vals, mid_z, 
         for W, b in color_module.effective_weights():
             col += [W, b]
     meta = dict(use_albedo=use_albedo, cos_anneal_ratio=float(cos_anneal_ratio), mode=int(mode),
-                sample_dist=float(sample_dist), pk=pk)
+                sample_dist=float(sample_dist), pk=pk, dp_group=dp_group)
     o = rays_o.detach().float().contiguous()
     d = rays_d.detach().float().contiguous()
     needs_grad = torch.is_grad_enabled() and (variance.requires_grad or any(t.requires_grad for t in flat + col))

@@ -3,7 +3,7 @@ parameter gradients per step (NCCL over NVLink / NVSwitch; gloo on CPU for the h
 
 The reference is single-process; this is what the north_star adds.  Parameters are replicated, every
 rank renders its own rays, `.grad` of all parameters are views into one flat fp32 buffer so the collective is a single
-`all_reduce(sum)` of 2.1-2.7 MB followed by a scale by 1/world.  Loss normalisers (mask_sum, the eikonal
+all-reduce of 2.1-2.7 MB (NCCL `ReduceOp.AVG`: the 1/world scale happens inside the collective).  Loss normalisers (mask_sum, the eikonal
 denominator) stay per-rank, i.e. DDP "mean of per-rank means" semantics.
 """
 from __future__ import annotations
@@ -65,15 +65,27 @@ class FlatGradAllReducer:
         self._collected = True
         return self.flat
 
+    def all_reduce_sum(self):
+        """Gather into the flat buffer and SUM over the ranks (ExactBatch: every rank's loss is its share of one global-
+        batch loss, so the shares add)."""
+        self.collect()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        return self.flat
+
     def all_reduce(self):
-        """Gather into the flat buffer, sum over ranks, divide by the world size.  One collective per step."""
+        """Gather into the flat buffer and average over the ranks: ONE collective per step and nothing else -- NCCL
+        averages inside the all-reduce (ReduceOp.AVG); gloo (CPU tests) has no AVG, there it is a sum and a scale."""
         self.collect()
         if not (dist.is_available() and dist.is_initialized()):
             return self.flat
         world = dist.get_world_size(self.group)
         if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / world)
+            if self.flat.is_cuda and dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / world)
         return self.flat
 
     @property
@@ -85,3 +97,53 @@ def rank_seed(iter_i: int, rank: int, world: int) -> int:
     """The reference reseeds with manual_seed(iter_i) every iteration (exp_runner.py:170); under data parallelism
     every rank must draw different pixels, so the seed is offset by the rank."""
     return iter_i * world + rank
+
+
+class ExactBatch:
+    """Optional exact global-batch equivalence ("or all-reduce the two scalars first").
+
+    With plain DDP semantics each rank normalises its loss by its own batch: the colour term by its own mask_sum
+    (exp_runner.py:194, 247), the eikonal term by its own count of points inside the relaxed sphere
+    (models/renderer.py:540) -- N ranks x B rays then differ from one N*B-ray batch by O(1/B).  ExactBatch removes that:
+
+        eb = ExactBatch(renderer)                    # renderer.dp_exact_group = the group: eikonal num / den summed over ranks
+        out = renderer.render_rnb(...)               # out['gradient_error'] is the GLOBAL mean on every rank
+        loss = eb.loss(out, true_rgb, mask, igr_weight, mask_weight)      # this rank's share of the global-batch loss
+        loss.backward(); reducer.all_reduce_sum()    # shares add: SUM, not mean
+
+    `loss` = colour L1 sum of this rank / (global mask_sum * L) + igr * (global eikonal mean, differentiated through this
+    rank's points) + mask_weight * local BCE sum / (global ray count); its gradients summed over the ranks equal the gradient
+    of the reference loss on the concatenated batch (checked under NCCL with the real kernels by bench.py's dp_check)."""
+
+    def __init__(self, renderer, group=None):
+        self.group = group
+        self.renderer = renderer
+        renderer.dp_exact_group = group if group is not None else True
+
+    def world(self):
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def loss(self, out, true_rgb, mask, igr_weight=0.1, mask_weight=0.1):
+        import torch.nn.functional as F
+        world = self.world()
+        norm = torch.stack([mask.sum(), torch.tensor(float(mask.shape[0]), device=mask.device)])
+        if world > 1:
+            dist.all_reduce(norm, op=dist.ReduceOp.SUM, group=self.group)
+        mask_sum, n_rays = norm[0] + 1e-5, norm[1]
+        err = ((out["color_fine"] - true_rgb) * mask[None, :, :]).reshape(-1, 3)
+        color = F.l1_loss(err, torch.zeros_like(err), reduction="sum") / (mask_sum * true_rgb.shape[0])
+        bce = F.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), mask, reduction="sum") / n_rays
+        # gradient_error is the global ratio on every rank and its backward is this rank's share of it; its VALUE would be
+        # counted `world` times by the sum over ranks, which does not matter for the gradients (and the logged loss is
+        # reported by total()).
+        return color + out["gradient_error"] * igr_weight + bce * mask_weight
+
+    def total(self, loss, out, igr_weight=0.1):
+        """The global-batch loss value from the per-rank shares (for logging): sum of shares minus the (world - 1) extra
+        copies of the eikonal term."""
+        world = self.world()
+        t = loss.detach().clone()
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t = t - (world - 1) * igr_weight * out["gradient_error"].detach()
+        return t

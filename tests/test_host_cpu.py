@@ -195,6 +195,76 @@ def test_data_parallel_allreduce_gloo_world2():
     assert np.allclose(res[0][1], ref, atol=1e-6)
 
 
+def _exact_worker(rank, world, port, q):
+    """ExactBatch host logic on CPU: a stand-in 'renderer' (tiny differentiable net) whose eikonal-like term is a ratio of
+    sums over the batch; the per-rank loss shares, gradient shares summed with all_reduce_sum."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "rnb-neus-fork_b200"))
+    from rnb_b200.parallel import ExactBatch, FlatGradAllReducer
+    torch.manual_seed(0)
+    net = torch.nn.Linear(4, 5)
+    red = FlatGradAllReducer(list(net.parameters()))
+    g = torch.Generator().manual_seed(10 + rank)
+    B = 6 + rank                                         # unequal batches: the normalisers really are global
+    x = torch.randn(B, 4, generator=g)
+    true_rgb = torch.rand(3, B, 3, generator=g)
+    mask = (torch.rand(B, 1, generator=g) < 0.6).float()
+
+    class R:
+        dp_exact_group = None
+    eb = ExactBatch(R)
+    h = net(x)
+    num, den = (h[:, 4] ** 2).sum(), torch.tensor(float(B))
+    both = torch.stack([num.detach(), den])
+    dist.all_reduce(both)
+    eik = num / (both[1] + 1e-5) + (both[0] - num.detach()) / (both[1] + 1e-5)      # global ratio, differentiable through local points
+    out = dict(color_fine=h[:, :3].sigmoid()[None].expand(3, B, 3), weight_sum=h[:, 3:4].sigmoid(), gradient_error=eik)
+    red.zero()
+    share = eb.loss(out, true_rgb, mask)
+    share.backward()
+    flat = red.all_reduce_sum().clone()
+    total = eb.total(share, out)
+    q.put((rank, flat.numpy(), x.numpy(), true_rgb.numpy(), mask.numpy(), float(total)))
+    dist.destroy_process_group()
+
+
+def test_exact_batch_shares_sum_to_the_global_batch_gradient_gloo_world2():
+    """parallel.ExactBatch: per-rank loss shares with global normalisers (mask_sum, ray count, eikonal denominator) + SUM of
+    the gradient shares == the reference loss (exp_runner.py:241-256) on the concatenated batch, also for unequal batches."""
+    import torch.multiprocessing as mp
+    import torch.nn.functional as F
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_exact_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert np.allclose(res[0][1], res[1][1])
+    torch.manual_seed(0)
+    net = torch.nn.Linear(4, 5)
+    x = torch.from_numpy(np.concatenate([r[2] for r in res], 0))
+    rgb = torch.from_numpy(np.concatenate([r[3] for r in res], 1))
+    mask = torch.from_numpy(np.concatenate([r[4] for r in res], 0))
+    h = net(x)
+    B = x.shape[0]
+    color = h[:, :3].sigmoid()[None].expand(3, B, 3)
+    err = ((color - rgb) * mask[None]).reshape(-1, 3)
+    loss = (F.l1_loss(err, torch.zeros_like(err), reduction="sum") / ((mask.sum() + 1e-5) * 3)
+            + 0.1 * (h[:, 4] ** 2).sum() / (B + 1e-5) + 0.1 * F.binary_cross_entropy(h[:, 3:4].sigmoid().clip(1e-3, 1 - 1e-3), mask))
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy()
+    got = res[0][1][:ref.size]
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-7), np.abs(got - ref).max()
+    assert abs(res[0][5] - float(loss)) < 1e-5 * abs(float(loss))
+
+
 def _cpu_triangle_soup(u, x_lo, x_hi):
     """marching cubes with the generated tables on the cells x_lo <= x < x_hi of a small host lattice (test helper)"""
     from rnb_b200 import mc_tables as M
