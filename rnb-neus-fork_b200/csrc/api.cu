@@ -350,7 +350,7 @@ int rnb_sdf_bwd(const rnb_points_t* pts, const void* wblob, const float* aux, co
     const uint8_t* inl = (const uint8_t*)st_in;
     const uint8_t* sw = (const uint8_t*)st_w;
     float* cpart = (float*)(sc + L.cs_part);      // [2][2 dw_splits][256]: the two sums of the sdf row of W_8
-    const int cs_mul = fused ? 1 : 2;             // column-sum partials per split (dw_gemm_kernel: one per warp group)
+    const int cs_mul = 2;                         // column-sum partials per split / worker: one per group of four warps
     const size_t cs_stride = (size_t)2 * L.dw_splits * 256;
     // layer 8 first: its CTAs take three column sums per tile and must not form the tail of the launch
     for (int li = 0; li < 9; ++li) {

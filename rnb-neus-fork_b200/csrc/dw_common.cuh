@@ -12,6 +12,26 @@ constexpr int DWC_RIDER_BYTES = 16384;    // 64 points x 128 columns fp16
 
 // Thread et (0..127) owns columns 2 et, 2 et + 1 (one 32-bit word of chunk et / 4) and walks the 64 point rows; the walk
 // starts at row `chunk`, so the 8 chunks x 4 words a warp touches per step fall into 32 different banks.
+// Producer lane, when it issues the stage of (pair pr, sub-tile sub): pull the 64 point weights of that sub-tile's weighted
+// sums towards L2.  They are read exactly once (d_sdf: 4 bytes per point), i.e. always cold; without the hint all eight
+// column-sum warps sat out a DRAM round trip per stage (the layer-8 CTAs ran 2.3x longer per stage than the others).
+__device__ __forceinline__ void dw_prefetch_weights(const DwJob& job, int pr, int sub) {
+#pragma unroll
+    for (int s = 0; s < DW_MAX_CS; ++s) {
+        if (s >= job.n_cs || job.cs[s].pair != pr || job.cs[s].n_w == 0) continue;
+        const DwColsum& c = job.cs[s];
+        if ((int64_t)sub * 64 >= c.n_valid) continue;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < c.n_w) {
+                const float* w = c.w[k] + (int64_t)sub * 64;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(w));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(w + 32));
+            }
+        }
+    }
+}
+
 struct DwColsumAcc {
     float v[DW_MAX_CS][3][2];
     float ws[DW_MAX_CS][3];        // sums of the weights (only thread et == 0 of a spec with wsum_partial keeps them)

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_gemm_kernel(const __grid_con
                     const uint32_t slot = it % DW_STAGES, ph = (it / DW_STAGES) & 1;
                     const bool mma = pr < job.mma_pairs;
                     const uint8_t* rider = job.x[pr];
+                    dw_prefetch_weights(job, pr, sub);
                     mbar_wait(&empty[slot], ph ^ 1);
                     mbar_expect_tx(&full[slot], DW_STAGE_A + (mma ? b_bytes : 0u) + (rider ? (uint32_t)DWC_RIDER_BYTES : 0u));
                     uint8_t* dst = smem + slot * DW_STAGE;

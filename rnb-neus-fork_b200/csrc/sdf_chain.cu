@@ -721,6 +721,7 @@ __device__ __forceinline__ void fused_dw_worker(uint8_t* smem, const SdfBwdFused
                     for (int pr = 0; pr < job.n_pairs; ++pr, ++it) {
                         const uint32_t slot = it % FDW_STAGES, ph = (it / FDW_STAGES) & 1;
                         const bool mma = pr < job.mma_pairs;
+                        dw_prefetch_weights(job, pr, sub);
                         mbar_wait(&empty[slot], ph ^ 1);
                         stage_sub[slot] = sub;
                         const uint8_t* rider = job.x[pr];
@@ -763,11 +764,14 @@ __device__ __forceinline__ void fused_dw_worker(uint8_t* smem, const SdfBwdFused
             }
             umma_commit(acc_full);
         }
-    } else if (warp < 6) {
-        // the job's column sums (bias gradients, the sdf row of W_8) from the staged tiles: dw_common.cuh
+    } else if (warp != 6 && warp < 11) {
+        // the job's column sums (bias gradients, the sdf row of W_8) from the staged tiles (dw_common.cuh): warps 2-5 take the
+        // point rows 0-31 of every sub-tile, warps 7-10 rows 32-63 (warp 6 is the scout); afterwards each group dumps one
+        // 128-row half of the accumulator
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;            // 0..127
+        const int grp = warp > 6 ? 1 : 0;
+        const int et = ((warp - (grp ? 7 : 2)) & 3) * 32 + lane;            // 0..127: owner of columns 2 et, 2 et + 1
         DwColsumAcc cs;
         cs.clear();
         uint32_t it = 0;
@@ -777,8 +781,8 @@ __device__ __forceinline__ void fused_dw_worker(uint8_t* smem, const SdfBwdFused
             const uint32_t slot = it % FDW_STAGES, ph = (it / FDW_STAGES) & 1;
             mbar_wait(&full[slot], ph);
             if (stage_stop[slot]) break;
-            cs.stage<64>(job, (int)(it % (uint32_t)job.n_pairs), stage_sub[slot], smem + slot * FDW_STAGE, et,
-                         reinterpret_cast<float*>(smem + FDW_STAGES * FDW_STAGE + 256) + (warp - 2) * DWC_WBUF_FLOATS, 0);
+            cs.stage<32>(job, (int)(it % (uint32_t)job.n_pairs), stage_sub[slot], smem + slot * FDW_STAGE, et,
+                         reinterpret_cast<float*>(smem + FDW_STAGES * FDW_STAGE + 256) + (warp - 2) * DWC_WBUF_FLOATS, grp * 32);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
         }
@@ -786,25 +790,23 @@ __device__ __forceinline__ void fused_dw_worker(uint8_t* smem, const SdfBwdFused
         if (it > 0) {
             mbar_wait(acc_full, 0);
             tc_fence_after();
+            const int h = grp;
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h)
-#pragma unroll 1
-                for (int c0 = 0; c0 < nw; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + h * 256 + c0, v);
-                    tmem_ld_wait();
-                    float4* dst = reinterpret_cast<float4*>(out + (size_t)(h * 128 + row) * nw + c0);
+            for (int c0 = 0; c0 < nw; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + h * 256 + c0, v);
+                tmem_ld_wait();
+                float4* dst = reinterpret_cast<float4*>(out + (size_t)(h * 128 + row) * nw + c0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (c0 + 4 * j < nw)          // nw = 16: only the first 16 of the 32 loaded columns exist
-                            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                }
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + 4 * j < nw)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
         } else {
-            for (int h = 0; h < 2; ++h)
-                for (int c = 0; c < nw; ++c) out[(size_t)(h * 128 + row) * nw + c] = 0.f;
+            for (int c = 0; c < nw; ++c) out[(size_t)(grp * 128 + row) * nw + c] = 0.f;
         }
-        cs.store(job, rep, et);
+        cs.store(job, 2 * rep + grp, et);
     }
 }
 
@@ -819,7 +821,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) sdf_bwd_fused_kernel(const _
     if (is_dw) {
         if (threadIdx.x == 0) {
             uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FDW_STAGES * FDW_STAGE);
-            for (int i = 0; i < FDW_STAGES; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[FDW_STAGES + i], 1 + 4); }
+            for (int i = 0; i < FDW_STAGES; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[FDW_STAGES + i], 1 + 8); }
             mbar_init(&bars[2 * FDW_STAGES], 1);
             int* stop = reinterpret_cast<int*>(bars + 2 * FDW_STAGES + 1);
             for (int i = 0; i < 4 + FDW_FIFO + 2 + FDW_STAGES; ++i) stop[i] = 0;   // stage_stop[4], fifo[], tail, head, stage_sub[]
@@ -841,7 +843,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) sdf_bwd_fused_kernel(const _
     const uint32_t tmem = tmem_slot;
     if (P.dbg && threadIdx.x == 0) P.dbg[FUSED_MAX_WORKERS + blockIdx.x] = globaltimer_ns();
     if (is_dw) {
-        if (warp < 7) fused_dw_worker(smem, P, tmem);
+        if (warp < 11) fused_dw_worker(smem, P, tmem);
     } else {
         const int n_v = 2 * ((int)gridDim.x - P.n_dw);
         TileMap tm;

@@ -168,7 +168,14 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device.  torch.cuda.current_stream() builds a Python Stream
+    object (~18 us; 18 calls per 512-ray step were 0.3 ms of a host-bound 1.8 ms iteration): the raw query is ~100x cheaper."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -14,6 +14,16 @@ from . import lib as L
 FINE_SAMPLES = 128
 
 
+def _params_of(module):
+    """list(module.parameters()), cached on the module (walking the module tree every step showed up in the host profile of
+    the 512-ray iteration); parameters are never re-created on the hot path, only updated in place."""
+    ps = getattr(module, "_rnb_params", None)
+    if ps is None:
+        ps = list(module.parameters())
+        module._rnb_params = ps
+    return ps
+
+
 def _sdf_wb(sdf_module):
     eff = sdf_module.effective_weights()
     if len(eff) != 9:
@@ -34,7 +44,7 @@ def _pack_sdf(flat, device):
 
 def packed_sdf_nograd(sdf_module):
     """Packed operands for no_grad evaluation, cached until a parameter changes (version counters)."""
-    params = list(sdf_module.parameters())
+    params = _params_of(sdf_module)
     key = tuple((p.data_ptr(), p._version) for p in params)
     cache = getattr(sdf_module, "_rnb_packed", None)
     if torch.cuda.is_current_stream_capturing():
@@ -62,7 +72,7 @@ def fold_and_pack(sdf_module):
     with torch.no_grad():
         pk = _pack_sdf(flat, flat[0].device)
     if not torch.cuda.is_current_stream_capturing():
-        params = list(sdf_module.parameters())
+        params = _params_of(sdf_module)
         sdf_module._rnb_packed = (tuple((p.data_ptr(), p._version) for p in params), pk)
     return flat, pk
 
@@ -142,7 +152,7 @@ def albedo_forward(color_module, points, normals, view_dirs, feature_vectors):
 
 def packed_nerf(nerf_module):
     """Packed NeRF operands, cached until a parameter changes (version counters)."""
-    params = list(nerf_module.parameters())
+    params = _params_of(nerf_module)
     key = tuple((p.data_ptr(), p._version) for p in params)
     cache = getattr(nerf_module, "_rnb_packed", None)
     if torch.cuda.is_current_stream_capturing():
