@@ -1,6 +1,8 @@
 // Stand-alone probe: how many bytes per second can the SMs pull out of L2 with cp.async.bulk (the weight ring of the
 // chain kernels), as a function of slice size, slices in flight, CTAs per SM, working-set size -- and whether a
-// cluster-of-2 multicast (each CTA issues half a slice, both receive all of it) delivers more bytes per SM than unicast.
+// cluster-of-2 multicast (each CTA issues half a slice, both receive all of it; "mcast2"), one issuing lane per ring slot
+// ("lanes") or a slice fetched as 2 / 4 concurrent part copies ("split2/4") deliver more bytes per SM than one lane issuing
+// whole slices ("unicast").
 // The chain kernels' roofline rests on this number.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o l2bw_probe l2bw_probe.cu
 // Run:   ./l2bw_probe            (prints one line per configuration)
@@ -184,9 +186,9 @@ int main() {
                tbs, bytes / (ms * 1e-3) / (clk_khz * 1e3) / sm);
         fflush(stdout);
     };
-    const unsigned long long ws_list[] = {2ull << 20};
-    const int slice_list[] = {4096, 8192, 16384};
-    const int stage_list[] = {3, 6, 12};
+    const unsigned long long ws_list[] = {2ull << 20, 32ull << 20, 256ull << 20};
+    const int slice_list[] = {8192, 16384, 32768};
+    const int stage_list[] = {3, 6};
     for (unsigned long long ws : ws_list)
         for (int slice : slice_list)
             for (int stages : stage_list)
