@@ -320,6 +320,8 @@ def run_perray(args, wl):
     for name, (fn, bpr) in cases.items():
         ms = timed(fn)
         kernels[name] = dict(ms_per_launch=ms, bytes_per_ray=bpr, gbs=bpr * B / ms / 1e6, frac_of_hbm_peak=bpr * B / ms / 1e6 / pk["hbm"])
+        if name == "upsample":      # 600 B/ray against ~1.5 k instructions/ray: its roof is the instruction stream, not memory
+            kernels[name]["bound"] = "instruction issue (ncu: issue slots 65 % busy, profiles/r02_ncu_summary.md); the HBM fraction is context"
         if name.startswith("composite"):
             tot_bytes += bpr * B
             tot_ms += ms

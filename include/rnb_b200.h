@@ -73,7 +73,11 @@ RNB_API int rnb_sdf_fwd_grad(const rnb_points_t* pts, const void* wblob, const f
  * d_feat16 = the fp16 stream + d_feat16_meta = the device float[2] written by rnb_albedo_bwd (both NULL = zero).
  * st_*: the streams written by rnb_sdf_fwd_grad for the same points.  scratch: rnb_sdf_bwd_scratch_bytes(n).
  * dW, db: HOST arrays of 9 DEVICE pointers, dW[l] fp32 [out_l,in_l] row-major (256x39, 256x256, 256x256,
- * 217x256, 256x256 x4, 257x256), db[l] [out_l]; overwritten. */
+ * 217x256, 256x256 x4, 257x256), db[l] [out_l]; overwritten.
+ * Launches: absmax, the backward chain (sdf_bwd_data), the weight-gradient GEMM (dw_gemm: all 9 layers, every bias /
+ * sdf-row column sum taken from its staged tiles), one deterministic reduce.  Environment RNB_BWD_FUSED=1 runs the chain and
+ * the weight-gradient contraction as ONE launch instead (sdf_bwd_fused; same results to summation order, measured not
+ * faster: profiles/r02_notes.md); RNB_DW_REPL="3,4,4,4,4,4,4,4,2" sets its workers per layer. */
 RNB_API size_t rnb_sdf_bwd_scratch_bytes(int64_t n_pts);
 /* Diagnostics of the fused backward launch (env RNB_FUSED_DBG=1): byte offset inside `scratch` of uint64 [2][160]
  * globaltimer stamps (block end times, then block start times), indexed by block: blocks [0, n_workers) are the
