@@ -411,6 +411,18 @@ struct Epi {
 __device__ __forceinline__ size_t stream_off(int64_t p, int chunk, int nchunks) {
     return ((size_t)((p >> 6) * nchunks + chunk) * 64 + (size_t)(p & 63)) * 16;
 }
+// 256-wide streams with the point-dependent part of the address hoisted: row = stream_row(p) once per tile, then
+// address = base + row + chunk * 1024 (the chunk term folds into the load / store's immediate offset where the chunk index
+// is a compile-time constant, and is one shift-add otherwise; the general form cost ~6 integer instructions per access)
+__device__ __forceinline__ size_t stream_row(int64_t p) { return (size_t)(p >> 6) * 32768 + (size_t)(p & 63) * 16; }
+__device__ __forceinline__ uint4 ld_stream_r(const uint8_t* base_row, int chunk) {
+    return *reinterpret_cast<const uint4*>(base_row + (size_t)chunk * 1024);
+}
+__device__ __forceinline__ void st_stream_r(uint8_t* base_row, int chunk, uint4 v, bool keep = false) {
+    uint4* q = reinterpret_cast<uint4*>(base_row + (size_t)chunk * 1024);
+    if (keep) *q = v;
+    else __stcs(q, v);
+}
 // streams are written once and read by a later kernel (or many steps later): evict-first (.cs) keeps them from
 // pushing the prefetched operands of the next step out of L2
 __device__ __forceinline__ void st_stream(uint8_t* base, int64_t p, int chunk, int nchunks, uint4 v) {

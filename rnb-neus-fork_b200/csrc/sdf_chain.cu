@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
         const int c_last = ep.col0 + EPI_HALF_COLS - 16;
         for (int t = 0; t < n_my; ++t) {
             const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
+            const size_t prow = stream_row(p);
             const bool live = p < P.src.n_pts;
             float x[3];
             load_point(P.src, p, x);
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                 ep.wait_acc();
                 uint8_t* st_a_next = P.st_in + (size_t)l * SS;       // in_{l+1} = a_l
                 const bool keep_l = (P.keep_mask >> l) & 1;
+                uint8_t* ran = st_a_next + prow;
                 const float* bl = bias + l * 256;
                 ep.sweep_half_bias(bl, [&](int c0, const float (&z)[16]) {
 #pragma unroll
@@ -218,8 +220,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         ha.x = pack_h2(a[0], a[1]); ha.y = pack_h2(a[2], a[3]); ha.z = pack_h2(a[4], a[5]); ha.w = pack_h2(a[6], a[7]);
                         const int ch = (c0 >> 3) + q;
                         ep.st_a(ch, ha);
-                        if (keep_l) *reinterpret_cast<uint4*>(st_a_next + stream_off(p, ch, 32)) = ha;
-                        else st_stream(st_a_next, p, ch, 32, ha);
+                        st_stream_r(ran, ch, ha, keep_l);
                     }
                 });
                 if (l == 3 && ep.half == 1) emit_skip_pe(ep, x, st_a_next, p);
@@ -230,6 +231,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             {
                 const float* b8f = bias + 8 * 256;
                 uint8_t* st_w7 = P.st_w + (size_t)7 * SS;
+                uint8_t* rfeat = P.st_feat + prow;
+                uint8_t* rw7 = st_w7 + prow;
                 ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]) + bb[j];
                         uint4 hf;
                         hf.x = pack_h2(f[0], f[1]); hf.y = pack_h2(f[2], f[3]); hf.z = pack_h2(f[4], f[5]); hf.w = pack_h2(f[6], f[7]);
-                        st_stream(P.st_feat, p, ch, 32, hf);
+                        st_stream_r(rfeat, ch, hf);
                         if (P.out_full && live) {
                             float* o = P.out_full + (size_t)p * 257 + 1 + c0 + q * 8;
 #pragma unroll
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         const float2 w2 = sigmul_x2(s2, make_float2(ww[4], ww[5])), w3 = sigmul_x2(s3, make_float2(ww[6], ww[7]));
                         hw.x = pack_h2(w0.x, w0.y); hw.y = pack_h2(w1.x, w1.y); hw.z = pack_h2(w2.x, w2.y); hw.w = pack_h2(w3.x, w3.y);
                         ep.st_a(ch, hw);
-                        if (P.st_w) st_stream(st_w7, p, ch, 32, hw);
+                        if (P.st_w) st_stream_r(rw7, ch, hw);
                     }
                 });
             }
@@ -272,9 +275,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
             for (int l = 7; l >= 1; --l) {
                 const uint8_t* st_sp = P.st_in + (size_t)(l - 1) * SS;      // a_{l-1}; s_{l-1} = 1 - exp(-100 a)
                 uint8_t* st_wp = P.st_w + (size_t)(l - 1) * SS;
+                const uint8_t* rsp = st_sp + prow;
+                uint8_t* rwp = st_wp + prow;
                 uint4 hs_n[2];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_sp, p, (ep.col0 >> 3) + q, 32);
+                for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream_r(rsp, (ep.col0 >> 3) + q);
                 ep.wait_acc();
                 if (l == 7) {
                     // A (= w_7) is dead: the two halves of the row combine their parts of <a_7, W_8[0,:]>
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                     for (int q = 0; q < 2; ++q) hs_c[q] = hs_n[q];
                     if (c0 < c_last) {
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_sp, p, (c0 >> 3) + 2 + q, 32);
+                        for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream_r(rsp, (c0 >> 3) + 2 + q);
                     }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_grad_kernel(const __
                         const float2 w2 = sigmul_x2(s2, make_float2(u[4], u[5])), w3 = sigmul_x2(s3, make_float2(u[6], u[7]));
                         hw.x = pack_h2(w0.x, w0.y); hw.y = pack_h2(w1.x, w1.y); hw.z = pack_h2(w2.x, w2.y); hw.w = pack_h2(w3.x, w3.y);
                         ep.st_a(ch, hw);
-                        if (P.st_w) st_stream(st_wp, p, ch, 32, hw);
+                        if (P.st_w) st_stream_r(rwp, ch, hw);
                     }
                 });
                 if (l == 4) {
@@ -424,6 +429,7 @@ __device__ __forceinline__ void bwd_epilogue(Epi& ep, const SdfBwdParams& P, con
     for (int t = 0; t < tm.n; ++t) {
         const int64_t tile = tm.first + (int64_t)t * tm.stride;
         const int64_t p = tile * TILE_M + ep.row;
+        const size_t prow = stream_row(p);
         const bool live = p < P.src.n_pts;
         float x[3];
         load_point(P.src, p, x);
@@ -444,9 +450,11 @@ __device__ __forceinline__ void bwd_epilogue(Epi& ep, const SdfBwdParams& P, con
         for (int l = 0; l < 8; ++l) {
             const uint8_t* st_s = P.st_in + (size_t)l * SS;      // a_l; s_l = 1 - exp(-100 a_l)
             uint8_t* st_un = P.st_uin + (size_t)l * SS;          // uin_{l+1} = ua_bar_l
+            const uint8_t* rs = st_s + prow;
+            uint8_t* run = st_un + prow;
             uint4 hs_n[2];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_s, p, ch0 + q, 32);
+            for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream_r(rs, ch0 + q);
             if (P.thread_prefetch) prefetch_stream_chunks(st_s, p, ch0 + 2, P.thread_prefetch);
             ep.wait_acc();
             ep.sweep_half([&](int c0, const uint32_t (&v)[16]) {
@@ -455,13 +463,13 @@ __device__ __forceinline__ void bwd_epilogue(Epi& ep, const SdfBwdParams& P, con
                 for (int q = 0; q < 2; ++q) hs_c[q] = hs_n[q];
                 if (c0 < c_last) {
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream(st_s, p, (c0 >> 3) + 2 + q, 32);
+                    for (int q = 0; q < 2; ++q) hs_n[q] = ld_stream_r(rs, (c0 >> 3) + 2 + q);
                 }
                 if (P.thread_prefetch && (threadIdx.x & 7) == 0) {
                     const int pc = (c0 >> 3) + 2 + P.thread_prefetch;        // chunks already covered: up to +1+pf
                     if (pc + 1 < ch0 + 16) {
-                        prefetch_l2(st_s + stream_off(p, pc, 32));
-                        prefetch_l2(st_s + stream_off(p, pc + 1, 32));
+                        prefetch_l2(rs + (size_t)pc * 1024);
+                        prefetch_l2(rs + (size_t)(pc + 1) * 1024);
                     }
                 }
 #pragma unroll
@@ -481,8 +489,7 @@ __device__ __forceinline__ void bwd_epilogue(Epi& ep, const SdfBwdParams& P, con
                         ub[j] = pack_h2_sat(uu2.x, uu2.y);
                     }
                     const uint4 uu = make_uint4(ub[0], ub[1], ub[2], ub[3]);
-                    if (P.keep_streams) *reinterpret_cast<uint4*>(st_un + stream_off(p, ch, 32)) = uu;
-                    else st_stream(st_un, p, ch, 32, uu);
+                    st_stream_r(run, ch, uu, P.keep_streams != 0);
                     if (l < 7) ep.st_a(ch, uu);
                 }
             });
@@ -527,8 +534,12 @@ __device__ __forceinline__ void bwd_epilogue(Epi& ep, const SdfBwdParams& P, con
             const uint8_t* st_w = P.st_w + (size_t)l * SS;       // w_l = s_l ua_l
             const uint8_t* st_u = P.st_uin + (size_t)l * SS;     // uin_{l+1} = s_l wbar_l
             uint8_t* st_zb = P.st_zbar + (size_t)l * SS;
+            const uint8_t* rs = st_s + prow;
+            const uint8_t* rw = st_w + prow;
+            const uint8_t* ru = st_u + prow;
+            uint8_t* rzb = st_zb + prow;
             // one 16-byte chunk (8 columns) of each stream in flight ahead of the one being consumed
-            uint4 hs_n = ld_stream(st_s, p, ch0, 32), hw_n = ld_stream(st_w, p, ch0, 32), hu_n = ld_stream(st_u, p, ch0, 32);
+            uint4 hs_n = ld_stream_r(rs, ch0), hw_n = ld_stream_r(rw, ch0), hu_n = ld_stream_r(ru, ch0);
             if (P.thread_prefetch) {
                 prefetch_stream_chunks(st_s, p, ch0 + 1, P.thread_prefetch);
                 prefetch_stream_chunks(st_w, p, ch0 + 1, P.thread_prefetch);
@@ -541,15 +552,15 @@ __device__ __forceinline__ void bwd_epilogue(Epi& ep, const SdfBwdParams& P, con
                     const int ch = (c0 >> 3) + q;
                     const uint4 hs = hs_n, hw = hw_n, hu = hu_n;
                     if (ch + 1 < ch0 + 16) {
-                        hs_n = ld_stream(st_s, p, ch + 1, 32);
-                        hw_n = ld_stream(st_w, p, ch + 1, 32);
-                        hu_n = ld_stream(st_u, p, ch + 1, 32);
+                        hs_n = ld_stream_r(rs, ch + 1);
+                        hw_n = ld_stream_r(rw, ch + 1);
+                        hu_n = ld_stream_r(ru, ch + 1);
                     }
                     if (P.thread_prefetch && (threadIdx.x & 7) == 0 && ch + 1 + P.thread_prefetch < ch0 + 16) {
-                        const size_t off = stream_off(p, ch + 1 + P.thread_prefetch, 32);
-                        prefetch_l2(st_s + off);
-                        prefetch_l2(st_w + off);
-                        prefetch_l2(st_u + off);
+                        const size_t off = (size_t)(ch + 1 + P.thread_prefetch) * 1024;
+                        prefetch_l2(rs + off);
+                        prefetch_l2(rw + off);
+                        prefetch_l2(ru + off);
                     }
                     const uint32_t hsa[4] = {hs.x, hs.y, hs.z, hs.w}, hwa[4] = {hw.x, hw.y, hw.z, hw.w},
                                    hua[4] = {hu.x, hu.y, hu.z, hu.w};
@@ -568,8 +579,7 @@ __device__ __forceinline__ void bwd_epilogue(Epi& ep, const SdfBwdParams& P, con
                         zb[j] = pack_h2_sat(zz.x, zz.y);
                     }
                     const uint4 uz = make_uint4(zb[0], zb[1], zb[2], zb[3]);
-                    if (P.keep_streams) *reinterpret_cast<uint4*>(st_zb + stream_off(p, ch, 32)) = uz;
-                    else st_stream(st_zb, p, ch, 32, uz);
+                    st_stream_r(rzb, ch, uz, P.keep_streams != 0);
                     if (l > 0) ep.st_a(ch, uz);
                 }
             });
