@@ -148,8 +148,11 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
                 RNB_TR(0, it, 0, true);
                 mbar_wait(&s.empty[slot], ph ^ 1);
                 RNB_TR(0, it, 1, true);
+#ifdef RNB_TRACE
+                if (tab.weights_evict_last & 2) { mbar_arrive(&s.full[slot]); continue; }   // experiment: no copies, stale slot contents
+#endif
                 mbar_expect_tx(&s.full[slot], bytes);
-                if (tab.weights_evict_last) bulk_g2s_hint(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot], keep);
+                if (tab.weights_evict_last & 1) bulk_g2s_hint(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot], keep);
                 else bulk_g2s(s.ring + slot * STAGE_BYTES, src + (size_t)ks * bytes, bytes, &s.full[slot]);
                 RNB_TR(0, it, 2, true);
             }
@@ -177,6 +180,11 @@ __device__ __forceinline__ void chain_mma_warp(const ChainSmem& s, const ChainTa
     uint32_t slot = 0, ph = 0, sig = 0;
     const uint64_t a_desc0 = umma_desc(smem_u32(s.sA), TILE_M * 16, 128);
     const uint32_t ring_base = smem_u32(s.ring);
+#ifdef RNB_TRACE
+    unsigned long long* tab_trace = tab.trace;
+    uint32_t tr_it = 0;
+    const bool tr_lane = (threadIdx.x & 31) == 0;
+#endif
     for (int t = 0; t < n_my_tiles; ++t) {
         for (int st = 0; st < tab.n_steps; ++st, ++sig) {
             const uint32_t n = tab.steps[st].n;
@@ -185,10 +193,14 @@ __device__ __forceinline__ void chain_mma_warp(const ChainSmem& s, const ChainTa
             const uint64_t b_desc0 = umma_desc(ring_base, n * 16, 128);
             const uint32_t b_slab = (2 * n * 16) >> 4;          // one K=16 slab of the stage, in descriptor units
             const uint32_t acc0 = tab.steps[st].accumulate;
+            RNB_TR(2, sig, 0, tr_lane);
             mbar_wait(s.a_ready, sig & 1);
+            RNB_TR(2, sig, 1, tr_lane);
             tc_fence_after();
             for (int ks = 0; ks < nsl; ++ks) {
+                RNB_TR(1, tr_it, 0, tr_lane);
                 mbar_wait(&s.full[slot], ph);
+                RNB_TR(1, tr_it, 1, tr_lane);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
@@ -200,10 +212,15 @@ __device__ __forceinline__ void chain_mma_warp(const ChainSmem& s, const ChainTa
                     umma_commit(&s.empty[slot]);
                 }
                 __syncwarp();
+                RNB_TR(1, tr_it, 2, tr_lane);
+#ifdef RNB_TRACE
+                ++tr_it;
+#endif
                 if (++slot == RING_STAGES) { slot = 0; ph ^= 1; }
             }
             if (elect_one()) umma_commit(s.acc_full);
             __syncwarp();
+            RNB_TR(2, sig, 2, tr_lane);
         }
     }
 }

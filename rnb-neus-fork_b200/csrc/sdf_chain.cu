@@ -122,48 +122,53 @@ __device__ __noinline__ void emit_skip_pe(const Epi& ep, const float (&x)[3], ui
     write_skip_cols(ep, [&](int i) { return e[i]; }, stream, p);
 }
 
+// epilogue of K1 for the tiles of one (virtual) CTA
+__device__ __forceinline__ void sdf_fwd_epilogue(Epi& ep, const SdfFwdParams& P, const TileMap tm) {
+    const float* bias = P.aux;
+    const float* w8row = P.aux + AUX_W8ROW;
+    const float b8 = __ldg(P.aux + AUX_B8_0);
+    for (int t = 0; t < tm.n; ++t) {
+        const int64_t p = (tm.first + (int64_t)t * tm.stride) * TILE_M + ep.row;
+        float x[3];
+        load_point(P.src, p, x);
+        if (ep.half == 0) emit_in0(ep, x, nullptr, p);
+        ep.signal();
+        float part = 0.f;
+#pragma unroll 1
+        for (int l = 0; l < 8; ++l) {
+            ep.wait_acc();
+            if (l < 7) {
+                fwd_layer_plain(ep, bias + l * 256);
+                if (l == 3 && ep.half == 1) emit_skip_pe(ep, x, nullptr, p);
+                ep.signal();
+            } else {
+                part = fwd_layer_last(ep, bias + l * 256, w8row);
+            }
+        }
+        // sdf = <a_7, W_8[0,:]> + b_8[0]: the two column halves of a row meet through the (now dead) A buffer
+        if (ep.half == 1) *ep.xchg() = part;
+        ep.sync_epi();
+        if (ep.half == 0 && p < P.src.n_pts) P.out[p] = P.out_scale * (part + *ep.xchg() + b8);
+    }
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS, 2) sdf_fwd_kernel(const __grid_constant__ SdfFwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const ChainSmem s = chain_carve(smem, SDF_A_COLS);
     const uint32_t tmem = chain_setup(s);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const TileMap tm = tilemap_grid(P.n_tiles);
     if (warp == 0) {
-        if (lane == 0) chain_producer(s, P.tab, P.wblob, n_my);
+        if (lane == 0) chain_producer(s, P.tab, P.wblob, tm);
     } else if (warp == 1) {
-        chain_mma_warp(s, P.tab, tmem, n_my);
+        chain_mma_warp(s, P.tab, tmem, tm.n);
     } else {
         Epi ep;
         ep.init(s, tmem);
 #ifdef RNB_TRACE
         ep.tab_trace = P.tab.trace;
 #endif
-        const float* bias = P.aux;
-        const float* w8row = P.aux + AUX_W8ROW;
-        const float b8 = __ldg(P.aux + AUX_B8_0);
-        for (int t = 0; t < n_my; ++t) {
-            const int64_t p = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + ep.row;
-            float x[3];
-            load_point(P.src, p, x);
-            if (ep.half == 0) emit_in0(ep, x, nullptr, p);
-            ep.signal();
-            float part = 0.f;
-#pragma unroll 1
-            for (int l = 0; l < 8; ++l) {
-                ep.wait_acc();
-                if (l < 7) {
-                    fwd_layer_plain(ep, bias + l * 256);
-                    if (l == 3 && ep.half == 1) emit_skip_pe(ep, x, nullptr, p);
-                    ep.signal();
-                } else {
-                    part = fwd_layer_last(ep, bias + l * 256, w8row);
-                }
-            }
-            // sdf = <a_7, W_8[0,:]> + b_8[0]: the two column halves of a row meet through the (now dead) A buffer
-            if (ep.half == 1) *ep.xchg() = part;
-            ep.sync_epi();
-            if (ep.half == 0 && p < P.src.n_pts) P.out[p] = P.out_scale * (part + *ep.xchg() + b8);
-        }
+        sdf_fwd_epilogue(ep, P, tm);
     }
     chain_teardown(s, tmem);
 }
@@ -898,6 +903,14 @@ cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st)
         if (e != cudaSuccess) return e;
     }
     if (P.n_tiles == 0) return cudaSuccess;
+#ifdef RNB_TRACE
+    if (getenv("RNB_DBG_SOLO")) {      // experiment: one CTA per SM (shared memory request too large for two)
+        const int big = 120 * 1024;
+        cudaFuncSetAttribute((const void*)sdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        sdf_fwd_kernel<<<sm_count, CHAIN_THREADS, big, st>>>(P);
+        return cudaGetLastError();
+    }
+#endif
     sdf_fwd_kernel<<<chain_grid(P.n_tiles, sm_count), CHAIN_THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
