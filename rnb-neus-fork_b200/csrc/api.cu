@@ -229,6 +229,8 @@ int rnb_sdf_fwd(const rnb_points_t* pts, const void* wblob, const float* aux, fl
     table_forward(P.tab);
 #ifdef RNB_TRACE
     P.tab.trace = g_trace;
+#endif
+#if defined(RNB_TRACE) || defined(RNB_DBG_HOOKS)
     if (getenv("RNB_DBG_NOFILL")) P.tab.weights_evict_last |= 2;
 #endif
     P.out = out;

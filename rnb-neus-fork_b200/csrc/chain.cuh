@@ -148,7 +148,7 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const ChainTa
                 RNB_TR(0, it, 0, true);
                 mbar_wait(&s.empty[slot], ph ^ 1);
                 RNB_TR(0, it, 1, true);
-#ifdef RNB_TRACE
+#if defined(RNB_TRACE) || defined(RNB_DBG_HOOKS)
                 if (tab.weights_evict_last & 2) { mbar_arrive(&s.full[slot]); continue; }   // experiment: no copies, stale slot contents
 #endif
                 mbar_expect_tx(&s.full[slot], bytes);

@@ -903,7 +903,7 @@ cudaError_t launch_sdf_fwd(const SdfFwdParams& P, int sm_count, cudaStream_t st)
         if (e != cudaSuccess) return e;
     }
     if (P.n_tiles == 0) return cudaSuccess;
-#ifdef RNB_TRACE
+#if defined(RNB_TRACE) || defined(RNB_DBG_HOOKS)
     if (getenv("RNB_DBG_SOLO")) {      // experiment: one CTA per SM (shared memory request too large for two)
         const int big = 120 * 1024;
         cudaFuncSetAttribute((const void*)sdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
