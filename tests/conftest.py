@@ -42,3 +42,26 @@ def cosine(a, b):
     a = np.asarray(a, np.float64).ravel()
     b = np.asarray(b, np.float64).ravel()
     return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
+
+
+# ---- parity margins: the tolerance-bearing asserts of the GPU tests go through check(), which records how far inside
+# the bound the measured value is; the table is written at session end (gpurun_out/parity_margins.md on the GPU box)
+# so every loosened tolerance has its measured error next to it (profiles/r02_parity_margins.md is a committed copy).
+_MARGINS = []
+
+
+def check(name, value, tol):
+    value = float(value)
+    _MARGINS.append((name, value, float(tol)))
+    assert value < tol, (name, value, tol)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if not _MARGINS or not os.path.isdir(out_dir):
+        return
+    lines = ["| check | measured | bound | measured / bound |", "|---|---|---|---|"]
+    for name, v, t in _MARGINS:
+        lines.append(f"| {name} | {v:.3e} | {t:.2e} | {v / t:.2f} |")
+    with open(os.path.join(out_dir, "parity_margins.md"), "w") as f:
+        f.write("\n".join(lines) + "\n")

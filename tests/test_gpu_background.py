@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_l2
+from conftest import load_golden, rel_l2, check
 from gpu_common import build_nets
 from rnb_b200 import kernels as K
 from rnb_b200 import ops, synth
@@ -87,7 +87,7 @@ def test_render_with_background_identical_samples():
         assert rel_l2(out[mine].cpu().numpy(), g["out_" + key]) < 1e-3, (key, rel_l2(out[mine].cpu().numpy(), g["out_" + key]))
     assert tuple(out["weights"].shape) == (8, 160)
     # individual weights move by inv_s/10 x the SDF error; ray sums are checked above
-    assert rel_l2(out["weights"].cpu().numpy(), g["out_weights"]) < 5e-3
+    check("background render: individual sample weights vs reference", rel_l2(out["weights"].cpu().numpy(), g["out_weights"]), 2e-3)
     assert np.array_equal(out["inside"].cpu().numpy(), g["out_inside_sphere"])
     assert abs(float(eik[0] / (eik[1] + 1e-5)) / float(g["out_gradient_error"]) - 1) < 1e-3
 

@@ -6,10 +6,12 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import load_golden, rel_l2, cosine
+from conftest import load_golden, rel_l2, cosine, check
 from gpu_common import build_nets, np_state
 from oracle import rnb_oracle as O
 from rnb_b200 import synth
+
+TOL_OWN_SAMPLING = 1e-3      # north_star; measured worst 7.3e-4 (profiles/r02_parity_margins.md)
 
 pytestmark = pytest.mark.gpu
 
@@ -62,15 +64,17 @@ def test_render_rnb_golden(case):
     # (a) the public call with its own hierarchical sampling: ray-integrated outputs and the loss
     with FixedRand(torch.from_numpy(g["t_rand"])):
         out = fn(*args, cos_anneal_ratio=float(g["r"]), no_albedo=no_albedo)
-    # Importance samples are placed by inverting a CDF built from the coarse SDF; an SDF that agrees to 3e-4 moves
-    # them by ~1e-4, i.e. a slightly different quadrature of the same integrand (few samples span the surface).
-    # The identical-input comparison at 1e-3 is (b); here the tolerance covers the quadrature change.
+    # The importance samples come from the library's own sampling pass (fp16-operand SDF), so they sit ~1e-4 away from
+    # the reference's; the ray integrals still hold the north_star 1e-3 (measured worst 7.3e-4 over the six fixtures,
+    # profiles/r02_parity_margins.md; tests/test_oracle_golden.py::test_sampling_pass_sensitivity bounds the effect of
+    # such a shift in the float64 oracle).
     for k in ("color_fine", "weight_sum", "s_val"):
         assert tuple(out[k].shape) == g["out_" + k].shape, k
-        assert rel_l2(out[k].detach().cpu().numpy(), g["out_" + k]) < 5e-3, k
-    # the eikonal term is a mean over the sample positions themselves; with 16 rays the fp32-level sampling noise of
-    # rays that miss (see test_oracle_golden) moves it by a fraction of a percent -- checked tightly in (b)
-    assert abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1) < 2e-2
+        check(f"e2e[{case}] public call, own sampling: {k} vs reference", rel_l2(out[k].detach().cpu().numpy(), g["out_" + k]), TOL_OWN_SAMPLING)
+    # the eikonal term is a mean over the sample positions themselves; rays that miss the surface have flat weight
+    # profiles, so a 1e-4 SDF difference in the sampling pass moves their importance samples a lot and the 16-ray mean by
+    # up to ~5e-3 (the oracle shows the same sensitivity: test_sampling_pass_sensitivity) -- checked at 1e-3 in (b)
+    check(f"e2e[{case}] public call, own sampling: eikonal term vs reference", abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1), 1e-2)
     loss_a = loss_fn(out, cu(g["true_rgb"]), cu(g["mask_used"]), float(g["mask_weight"]))
     assert abs(float(loss_a) / float(g["loss"]) - 1) < 1e-3
     # (b) identical inputs for the fine pass (the reference's own z_vals): per-sample outputs are comparable only
@@ -82,8 +86,8 @@ def test_render_rnb_golden(case):
         # list and cannot be: alpha differences two sigmoids of inv_s * sdf, so an SDF that is right to 3e-4
         # relative moves a single weight by inv_s/10 times that; the ray sums (colour, weight_sum) stay at 1e-3.
         tol = 1e-2 if k in ("weights", "weight_max") else 1e-3
-        assert rel_l2(out[k].detach().cpu().numpy(), g["out_" + k]) < tol, k
-    assert abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1) < 1e-3
+        check(f"e2e[{case}] reference z_vals: {k} vs reference", rel_l2(out[k].detach().cpu().numpy(), g["out_" + k]), tol)
+    check(f"e2e[{case}] reference z_vals: eikonal term", abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1), 1e-3)
     mism = (out["inside_sphere"].cpu().numpy() != g["out_inside_sphere"]).mean()
     assert mism < 1e-3
     loss = loss_fn(out, cu(g["true_rgb"]), cu(g["mask_used"]), float(g["mask_weight"]))
@@ -117,17 +121,20 @@ def test_render_rnb_golden(case):
             # 100 %.  Summed over the 2048 points of this fixture that leaves 1-2 % on its first-layer gradients
             # (3e-2 here); test_render_rnb_oracle_large checks 1e-2 at a realistic point count.
             single = float(np.abs(ref).max()) ** 2 > 0.99 * float((ref.astype(np.float64) ** 2).sum())
-            # Per-tensor bound on this 16-ray fixture: 2e-2 (weight_g gradients are row-wise projections of dW onto v
-            # with cancellation; they sit at ~1e-2 with so few contributing points).  The north_star bound 1e-2 is
-            # asserted on the whole parameter vector below and per tensor in test_render_rnb_oracle_large.
-            tol = 1e-1 if single else (3e-2 if tag == "color" else 2e-2)
+            # Per-tensor bounds on this 16-ray fixture, set from the measured errors (profiles/r02_parity_margins.md): SDF
+            # tensors 1.25e-2 (worst 8.5e-3: weight_g gradients are row-wise projections of dW onto v with cancellation and
+            # few contributing points), albedo net 2e-2 (worst 1.5e-2, relu flips), one-element tensors 8e-2 (worst 5.8e-2).
+            # The north_star bound 1e-2 is asserted on the whole parameter vector below (measured 3.2e-3) and per tensor at
+            # 192 and 512 rays (test_render_rnb_oracle_large, tests/test_gpu_large.py).
+            tol = 8e-2 if single else (2e-2 if tag == "color" else 1.25e-2)
             assert cosine(got[::st], ref) > 0.999, (key, cosine(got[::st], ref))
-            assert rel_l2(got[::st], ref) < tol, (key, rel_l2(got[::st], ref))
+            check(f"e2e[{case}] gradient {key} (16 rays{', one-element tensor' if single else ''})", rel_l2(got[::st], ref), tol)
             assert abs(np.linalg.norm(got) / float(g[f"n_{tag}.{pname}"]) - 1) < tol, key
             n += 1
     assert n >= 16
     all_got, all_ref = np.concatenate(all_got), np.concatenate(all_ref)
-    assert cosine(all_got, all_ref) > 0.999 and rel_l2(all_got, all_ref) < 1e-2
+    assert cosine(all_got, all_ref) > 0.999
+    check(f"e2e[{case}] whole parameter-gradient vector (16 rays)", rel_l2(all_got, all_ref), 1e-2)
 
 
 @pytest.mark.parametrize("warm,no_albedo", [(True, False), (False, True)])
@@ -161,7 +168,7 @@ def test_render_rnb_oracle_large(warm, no_albedo):
                 continue
             single = float(np.abs(ref).max()) ** 2 > 0.99 * float((ref ** 2).sum())
             assert cosine(got, ref) > 0.999, (key, cosine(got, ref))
-            assert rel_l2(got, ref) < (5e-2 if single else 1e-2), (key, rel_l2(got, ref))
+            check(f"oracle192[warm={warm},no_albedo={no_albedo}] gradient {key}{' (one-element tensor)' if single else ''}", rel_l2(got, ref), 5e-3)        # north_star 1e-2; measured worst 2.1e-3
             worst = max(worst, rel_l2(got, ref))
     assert abs(float(var.variance.grad) / float(grads["variance"]) - 1) < 1e-2
     print("worst per-tensor rel-L2:", worst)

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_l2, cosine
+from conftest import load_golden, rel_l2, cosine, check
 from gpu_common import build_nets, np_state
 from rnb_b200 import synth
 from test_gpu_e2e import make_renderer, loss_fn, cu, FixedRand
@@ -33,7 +33,7 @@ def test_render_rnb_512_reference_and_oracle(case):
     out = renderer._render_rnb(warm, *args, -1, None, r, no_albedo, _z_vals=cu(g["z_vals"]))
     c = lambda t: t.detach().cpu().numpy()
     for k in ("color_fine", "weight_sum", "s_val"):
-        assert rel_l2(c(out[k]), g["out_" + k]) < 1e-3, (k, rel_l2(c(out[k]), g["out_" + k]))
+        check(f"512 rays[{case}] reference z_vals: {k} vs reference", rel_l2(c(out[k]), g["out_" + k]), 1e-3)
     assert rel_l2(c(out["gradients"][:32]), g["out_gradients_head"]) < 1e-3          # normals
     assert abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1) < 1e-3
     assert rel_l2(c(out["color_fine"]), g["o_color_fine"]) < 1e-3                     # ... and the float64 oracle
@@ -95,8 +95,10 @@ def test_render_rnb_512_reference_and_oracle(case):
     assert not bad, bad                # north_star: every tensor cos >= 0.999 and rel-L2 <= 1e-2, no exceptions
     assert n >= (26 if no_albedo else 34), n
     all_got, all_ref = np.concatenate(all_got), np.concatenate(all_ref)
-    assert cosine(all_got, all_ref) > 0.9999 and rel_l2(all_got, all_ref) < 5e-3
+    assert cosine(all_got, all_ref) > 0.9999
+    check(f"512 rays[{case}] whole parameter-gradient vector vs reference", rel_l2(all_got, all_ref), 5e-3)
     k_worst = max(worst, key=worst.get)
+    check(f"512 rays[{case}] worst single tensor ({k_worst})", worst[k_worst], 1.25e-2 if warm else 1e-2)
     print(f"{case}: worst per-tensor rel-L2 {worst[k_worst]:.2e} ({k_worst}); whole vector {rel_l2(all_got, all_ref):.2e}; "
           f"{n_flip} of {resid.numel()} L1 residuals change sign between the two forwards")
     # ---- (b) the public call with its own hierarchical sampling (same jitter): the importance samples come from inverting a
@@ -107,7 +109,7 @@ def test_render_rnb_512_reference_and_oracle(case):
     with FixedRand(torch.from_numpy(g["t_rand"])):
         out2 = fn(*args, cos_anneal_ratio=r, no_albedo=no_albedo)
     for k in ("color_fine", "weight_sum"):
-        assert rel_l2(c(out2[k]), g["out_" + k]) < 2e-3, (k, rel_l2(c(out2[k]), g["out_" + k]))
+        check(f"512 rays[{case}] public call, own sampling: {k} vs reference", rel_l2(c(out2[k]), g["out_" + k]), 2e-3 if k == "color_fine" else 1e-3)
     loss2 = loss_fn(out2, b["true_rgb"], mask, float(g["mask_weight"]))
     assert abs(float(loss2) / float(g["loss"]) - 1) < 1e-3
 
