@@ -1,4 +1,4 @@
-"""Runs the UNMODIFIED reference (models/renderer.py:828-930 render_rnb_warmup + the loss of exp_runner.py:240-260) through
+"""Runs the UNMODIFIED reference (models/renderer.py:828-930 render_rnb_warmup / 932-1033 render_rnb + the loss of exp_runner.py:240-260) through
 PyTorch-CUDA, fp32 with TF32 off, on the benchmark's own batch -- 8192 rays, 1 048 576 fine points, "trained-like" perturbed
 weights -- and writes its outputs, its own sample depths, the loss and every parameter gradient to an npz.  Started as a
 subprocess by tests/test_gpu_fullsize.py: the reference needs the process-wide
@@ -16,6 +16,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--out", required=True)
 ap.add_argument("--rays", type=int, default=8192)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--warm", type=int, default=1)
+ap.add_argument("--no-albedo", type=int, default=0)
 args = ap.parse_args()
 
 from oracle.gen_golden import build_reference_nets, injected_rand, loss_fn  # noqa: E402
@@ -29,7 +31,8 @@ for m in (nerf, sdf, var, col):
     m.to(dev)
 renderer = ref.renderer.NeuSRenderer(nerf, sdf, var, col, **synth.WMASK_CONF["neus_renderer"])
 renderer.color_depth = 3
-b = {k: v.to(dev) for k, v in synth.make_batch(args.rays, 3, True, args.seed).items()}
+warm, no_albedo = bool(args.warm), bool(args.no_albedo)
+b = {k: v.to(dev) for k, v in synth.make_batch(args.rays, 3, warm, args.seed).items()}
 captured = {}
 orig_core = renderer.render_core_mvps
 
@@ -42,8 +45,8 @@ def core(rays_o, rays_d, z_vals, *a, **k):
 renderer.render_core_mvps = core
 torch.set_default_tensor_type("torch.cuda.FloatTensor")
 with torch.device(dev), injected_rand([b["t_rand"] + 0.5]):
-    out = renderer.render_rnb_warmup(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"], cos_anneal_ratio=1.0,
-                                     no_albedo=False)
+    fn = renderer.render_rnb_warmup if warm else renderer.render_rnb
+    out = fn(b["rays_o"], b["rays_d"], b["near"], b["far"], b["lights_dir"], cos_anneal_ratio=1.0, no_albedo=no_albedo)
     loss = loss_fn(out, b["true_rgb"], b["mask"], 0.1, 0.1, 3)[0]
     loss.backward()
 torch.cuda.synchronize()
