@@ -18,6 +18,7 @@ ap.add_argument("--rays", type=int, default=8192)
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--no-albedo", type=int, default=0)
+ap.add_argument("--grid", type=int, default=0, help="instead of a train step: extract_fields at this resolution -> .npy")
 args = ap.parse_args()
 
 from oracle.gen_golden import build_reference_nets, injected_rand, loss_fn  # noqa: E402
@@ -31,6 +32,20 @@ for m in (nerf, sdf, var, col):
     m.to(dev)
 renderer = ref.renderer.NeuSRenderer(nerf, sdf, var, col, **synth.WMASK_CONF["neus_renderer"])
 renderer.color_depth = 3
+if args.grid:
+    # validate_mesh's lattice (exp_runner.py:561-578 -> models/renderer.py:10-25, 1219-1224) with the reference's own code
+    import time
+    torch.set_default_tensor_type("torch.cuda.FloatTensor")
+    bmin = torch.tensor([-1.01, -1.01, -1.01])
+    bmax = torch.tensor([1.01, 1.01, 1.01])
+    torch.cuda.synchronize()
+    t0 = time.time()
+    with torch.device(dev):
+        u = ref.renderer.extract_fields(bmin, bmax, args.grid, lambda pts: -sdf.sdf(pts))
+    dt = time.time() - t0
+    np.save(args.out, u)
+    print("REF_DONE grid", args.grid, "seconds", round(dt, 2))
+    sys.exit(0)
 warm, no_albedo = bool(args.warm), bool(args.no_albedo)
 b = {k: v.to(dev) for k, v in synth.make_batch(args.rays, 3, warm, args.seed).items()}
 captured = {}

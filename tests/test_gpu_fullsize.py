@@ -93,3 +93,32 @@ def test_8192_rays_against_the_reference_on_the_same_gpu(tmp_path, warm, no_albe
     check(f"{tagc}, public call (own sampling): loss", abs(float(loss2) / float(g["loss"]) - 1), 1e-3)
     print(f"{tagc}: worst tensor {worst[1]} {worst[0]:.2e}; whole vector {rel_l2(all_got, all_ref):.2e}; "
           f"{int(flipped.sum())} of {resid.numel()} L1 residuals flip; reference peak memory {float(g['peak_mem_gb']):.1f} GB")
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present (run oracle/stage_reference.py)")
+def test_512_lattice_against_the_reference_on_the_same_gpu(tmp_path):
+    """BASELINE.json configs[4]: the whole 512^3 lattice of validate_mesh (134 M queries) from the reference's own
+    extract_fields (models/renderer.py:10-25) through PyTorch-CUDA vs the grid mode of K1: every node, not a sample."""
+    from rnb_b200 import grid
+    from gpu_common import build_nets
+    R = 512
+    path = str(tmp_path / "ref_u512.npy")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_cuda_fullsize.py"), "--out", path, "--grid", str(R)],
+                       capture_output=True, text=True, timeout=1200)
+    assert p.returncode == 0 and "REF_DONE" in p.stdout, (p.stdout + p.stderr)[-2000:]
+    ref = np.load(path)
+    assert ref.shape == (R, R, R) and ref.dtype == np.float32
+    _, sdf, _, _ = build_nets(True)
+    u = grid.sdf_slab(sdf, [-1.01] * 3, [1.01] * 3, R, 0, R)
+    torch.cuda.synchronize()
+    r = torch.from_numpy(ref).cuda()
+    diff = (u - r).double()
+    check("512^3 lattice vs reference (CUDA fp32): rel-L2 over all 134 M nodes", float(diff.norm() / r.double().norm()), 1e-3)
+    check("512^3 lattice vs reference: max |difference| / max |u|", float(diff.abs().max() / r.abs().max()), 1e-3)
+    # what marching cubes consumes is the sign: nodes whose sign differs must be numerically on the surface
+    flip = torch.sign(u) != torch.sign(r)
+    n_flip = int(flip.sum())
+    worst = float(r[flip].abs().max()) if n_flip else 0.0
+    check("512^3 lattice vs reference: largest |u_ref| among nodes whose sign differs", worst, 3e-4)     # measured 1.5e-4 (927 nodes)
+    assert n_flip < 1e-5 * R ** 3, n_flip
+    print(f"512^3 lattice: {n_flip} of {R ** 3} nodes change sign (largest |u_ref| among them {worst:.1e}); " + p.stdout.strip().splitlines()[-1])
