@@ -18,6 +18,7 @@ ap.add_argument("--rays", type=int, default=8192)
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--no-albedo", type=int, default=0)
+ap.add_argument("--bg", type=int, default=0, help="instead of a train step: render() with the NeRF++ background, n_outside = 32")
 ap.add_argument("--grid", type=int, default=0, help="instead of a train step: extract_fields at this resolution -> .npy")
 args = ap.parse_args()
 
@@ -45,6 +46,38 @@ if args.grid:
     dt = time.time() - t0
     np.save(args.out, u)
     print("REF_DONE grid", args.grid, "seconds", round(dt, 2))
+    sys.exit(0)
+if args.bg:
+    # NeuSRenderer.render() with n_outside = 32 (models/renderer.py:556-648), forward only like its one reference caller
+    synth.perturb_state_dict_(nerf, 0.02, 7)
+    conf = dict(synth.WMASK_CONF["neus_renderer"], n_outside=32)
+    renderer = ref.renderer.NeuSRenderer(nerf, sdf, var, col, **conf)
+    renderer.color_depth = 3
+    b = {k: v.to(dev) for k, v in synth.make_batch(args.rays, 3, True, args.seed).items()}
+    r2 = torch.rand(args.rays, 32, generator=torch.Generator().manual_seed(14)).to(dev)
+    cap = {}
+    core0, outside0 = renderer.render_core, renderer.render_core_outside
+
+    def core_hook(rays_o, rays_d, z_vals, *a, **k):
+        cap["z_vals"] = z_vals.detach().clone()
+        return core0(rays_o, rays_d, z_vals, *a, **k)
+
+    def outside_hook(rays_o, rays_d, z_vals, *a, **k):
+        cap["z_feed"] = z_vals.detach().clone()
+        return outside0(rays_o, rays_d, z_vals, *a, **k)
+
+    renderer.render_core, renderer.render_core_outside = core_hook, outside_hook
+    torch.set_default_tensor_type("torch.cuda.FloatTensor")
+    with torch.device(dev), injected_rand([b["t_rand"] + 0.5, r2]):       # (render() differentiates the SDF itself: no no_grad)
+        out = renderer.render(b["rays_o"], b["rays_d"], b["near"], b["far"], cos_anneal_ratio=1.0, background_rgb=None)
+    torch.cuda.synchronize()
+    c = lambda t: t.detach().float().cpu().numpy()
+    d = dict(seed=np.array(args.seed), rand_outside=c(r2), z_vals=c(cap["z_vals"]), z_feed=c(cap["z_feed"]))
+    for k in ("color_fine", "weight_sum", "weight_max", "weights", "cdf_fine", "s_val", "gradient_error", "inside_sphere"):
+        d["out_" + k] = c(out[k])
+    d["out_gradients_head"] = c(out["gradients"][:64])
+    np.savez(args.out, **d)
+    print("REF_DONE render() with background,", args.rays, "rays")
     sys.exit(0)
 warm, no_albedo = bool(args.warm), bool(args.no_albedo)
 b = {k: v.to(dev) for k, v in synth.make_batch(args.rays, 3, warm, args.seed).items()}

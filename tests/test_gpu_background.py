@@ -98,12 +98,12 @@ def test_render_public_call_with_background():
     with RandQueue([torch.from_numpy(g["t_rand"]) + 0.5, torch.from_numpy(g["rand_outside"])]):
         out = r.render(cu(g["rays_o"]), cu(g["rays_d"]), cu(g["near"]), cu(g["far"]), cos_anneal_ratio=1.0,
                        background_rgb=None)
-    # own hierarchical sampling: a slightly different quadrature of the same integrand (see test_gpu_e2e)
+    # own hierarchical sampling: the ray integrals hold 1e-3 (measured 2e-5); the eikonal mean over 8 rays moves by 2e-3 (see test_gpu_e2e)
     for k in ("color_fine", "weight_sum", "s_val"):
         assert tuple(out[k].shape) == g["out_" + k].shape, k
-        assert rel_l2(out[k].cpu().numpy(), g["out_" + k]) < 5e-3, k
+        check(f"background public call (8 rays, own sampling): {k}", rel_l2(out[k].cpu().numpy(), g["out_" + k]), 1e-3)
     assert tuple(out["weights"].shape) == (8, 160) and tuple(out["inside_sphere"].shape) == (8, 128)
-    assert abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1) < 2e-2
+    check("background public call (8 rays, own sampling): eikonal term", abs(float(out["gradient_error"]) / float(g["out_gradient_error"]) - 1), 1e-2)
     # white background term (reference :266-267)
     with RandQueue([torch.from_numpy(g["t_rand"]) + 0.5, torch.from_numpy(g["rand_outside"])]):
         out_w = r.render(cu(g["rays_o"]), cu(g["rays_d"]), cu(g["near"]), cu(g["far"]), cos_anneal_ratio=1.0,

@@ -122,3 +122,37 @@ def test_512_lattice_against_the_reference_on_the_same_gpu(tmp_path):
     check("512^3 lattice vs reference: largest |u_ref| among nodes whose sign differs", worst, 3e-4)     # measured 1.5e-4 (927 nodes)
     assert n_flip < 1e-5 * R ** 3, n_flip
     print(f"512^3 lattice: {n_flip} of {R ** 3} nodes change sign (largest |u_ref| among them {worst:.1e}); " + p.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present (run oracle/stage_reference.py)")
+def test_render_with_background_8192_rays_against_the_reference_on_the_same_gpu(tmp_path):
+    """NeuSRenderer.render() with the NeRF++ background (n_outside = 32, models/renderer.py:556-648; BASELINE config 3's
+    womask flavour), forward only like its one reference caller, at 8192 rays x (128 + 32) samples."""
+    from rnb_b200 import kernels as K, ops
+    from test_gpu_background import make_bg_renderer, RandQueue
+    B = 8192
+    path = str(tmp_path / "ref_bg.npz")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_cuda_fullsize.py"), "--out", path, "--rays", str(B), "--bg", "1"],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "REF_DONE" in p.stdout, (p.stdout + p.stderr)[-2000:]
+    g = dict(np.load(path))
+    r = make_bg_renderer()
+    b = {k: v.cuda() for k, v in synth.make_batch(B, 3, True, int(g["seed"])).items()}
+    # (a) the reference's own sample depths, inside and outside the sphere
+    z_vals = cu(g["z_vals"])
+    _, mid = K.final_merge(z_vals, None, 2.0 / 64)
+    out = ops.render_with_background(r, b["rays_o"], b["rays_d"], z_vals, mid, cu(g["z_feed"][:, 128:]), 1.0, 2.0 / 64)
+    c = lambda t: t.detach().cpu().numpy()
+    for mine, key in (("color", "color_fine"), ("weight_sum", "weight_sum"), ("cdf", "cdf_fine")):
+        check(f"render() with background, 8192 rays, reference depths: {key}", rel_l2(c(out[mine]), g["out_" + key]), 1e-3)
+    check("render() with background, 8192 rays, reference depths: normals of 64 rays", rel_l2(c(out["gradients"][:64]), g["out_gradients_head"]), 1e-3)
+    check("render() with background, 8192 rays, reference depths: individual weights", rel_l2(c(out["weights"]), g["out_weights"]), 1e-2)
+    eik = out["eik_part"].sum(0)
+    check("render() with background, 8192 rays, reference depths: eikonal term", abs(float(eik[0] / (eik[1] + 1e-5)) / float(g["out_gradient_error"]) - 1), 1e-3)
+    mism = float((c(out["inside"]) != g["out_inside_sphere"]).mean())
+    assert mism < 1e-4, mism
+    # (b) the public call, own sampling, the same two random draws
+    with RandQueue([b["t_rand"].cpu() + 0.5, torch.from_numpy(g["rand_outside"])]):
+        out2 = r.render(b["rays_o"], b["rays_d"], b["near"], b["far"], cos_anneal_ratio=1.0, background_rgb=None)
+    check("render() with background, 8192 rays, public call: color_fine", rel_l2(c(out2["color_fine"]), g["out_color_fine"]), 1e-3)
+    check("render() with background, 8192 rays, public call: weight_sum", rel_l2(c(out2["weight_sum"]), g["out_weight_sum"]), 1e-3)
